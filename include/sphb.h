@@ -90,6 +90,11 @@ size_t sphb_sizeof_particle(int dim);
  * sphb_upload_aos takes the GLOBAL particle set on every rank; each rank computes a contiguous
  * Morton-curve slice of it and the stage calls exchange what the other ranks need. */
 int sphb_set_distributed(sphb_ctx *ctx, int rank, int world, void *nccl_comm);
+/* Same, but the library creates (and owns) the communicator: rank 0 calls sphb_nccl_unique_id,
+ * ships the 128 bytes to the other ranks by any means (MPI, torch.distributed, a file), and every
+ * rank calls sphb_set_distributed_id with them (ncclCommInitRank inside; libnccl is dlopen'ed). */
+int sphb_nccl_unique_id(void *out128);
+int sphb_set_distributed_id(sphb_ctx *ctx, int rank, int world, const void *unique_id128);
 
 /* ---- state transfer (Simulation::get_particles(), include/simulation.hpp:25) ------------- */
 
@@ -218,6 +223,10 @@ int sphb_get_timers(sphb_ctx *ctx, float ms[SPHB_T_COUNT]);
 
 /* Number of kernel launches issued by this context since creation. */
 uint64_t sphb_launch_count(const sphb_ctx *ctx);
+/* Particles whose Newton-Raphson smoothing-length iteration did not converge since creation (the
+ * reference only logs "Particle id N is not convergence", src/pre_interaction.cpp:277-280, and
+ * falls back to the guess; so does the device). */
+uint64_t sphb_nonconverged(const sphb_ctx *ctx);
 
 /* Pinned host memory for e2e transfers. */
 void *sphb_host_alloc(size_t bytes);

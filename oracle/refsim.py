@@ -77,9 +77,9 @@ def to_ref_params(p):
     return r
 
 
-def build(verbose=False):
-    """Compile the checkers (make -C oracle).  Building the checker is not using it."""
-    r = subprocess.run(["make", "-C", _HERE, "-j8"], capture_output=True, text=True)
+def build(target="all", verbose=False):
+    """Compile the checkers (make -C oracle [all|ref|port]).  Building the checker is not using it."""
+    r = subprocess.run(["make", "-C", _HERE, "-j8", target], capture_output=True, text=True)
     if verbose or r.returncode:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode:

@@ -1,0 +1,1081 @@
+// sphb_api.cu — the extern "C" layer of libsphb.so (declared in include/sphb.h).
+//
+// Host-side orchestration only: memory, the level loop of the tree build, kernel launches on the
+// context's stream, and the NCCL exchange of the multi-GPU mode.  All arithmetic lives in the
+// kernels of sphb_tree.cuh / sphb_stages.cuh.  There is no CPU fallback anywhere in this file.
+#include "../../include/sphb.h"
+#include "sphb_stages.cuh"
+
+#include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace sphb;
+
+namespace {
+
+std::string g_create_error;
+
+// ---- minimal NCCL binding (dlopen: single-GPU use must not need libnccl) ----------------------
+typedef struct ncclComm * ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclInt32 = 2, ncclInt = 2, ncclUint64 = 5, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
+struct NcclApi {
+    void * lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char * (*GetErrorString)(int) = nullptr;
+    bool load(std::string & err)
+    {
+        if (lib) return true;
+        const char * names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char * nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define NSYM(f) f = reinterpret_cast<decltype(f)>(dlsym(lib, "nccl" #f)); if (!f) { err = "libnccl lacks nccl" #f; return false; }
+        NSYM(GetUniqueId) NSYM(CommInitRank) NSYM(CommDestroy) NSYM(AllGather) NSYM(AllReduce) NSYM(GroupStart) NSYM(GroupEnd)
+        NSYM(GetErrorString)
+#undef NSYM
+        return true;
+    }
+} g_nccl;
+
+} // namespace
+
+struct sphb_ctx {
+    int dim = 0, device = 0;
+    sphb_params hp{};
+    DevParams P{};
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+
+    int n = 0;                 // particles
+    int n_pad = 0;             // array length (padded for the in-place all-gather)
+    PSoA cur{}, alt{};
+    std::vector<void *> allocs;            // everything freed at destroy / resize
+    int n_darr = 0, n_iarr = 0;
+    double ** d_ptr_cur = nullptr, ** d_ptr_alt = nullptr;      // device pointer tables for k_permute
+    int ** d_iptr_cur = nullptr, ** d_iptr_alt = nullptr;
+    bool cur_is_a = true;
+
+    unsigned long long * keys = nullptr, * keys_alt = nullptr;
+    int * idx = nullptr, * idx_alt = nullptr;
+    void * cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+
+    TreeBuild tb{}; TreeDev td{};
+    std::vector<void *> node_allocs;
+    int node_cap = 0;
+    std::vector<std::pair<int, int>> levels;
+    int * lvl_tmp = nullptr, * lvl_offs = nullptr;
+    bool tree_valid = false;
+
+    double * d_root = nullptr;             // centre[3], edge
+    double * d_bbox_part = nullptr; int bbox_blocks = 0;
+    double * d_scal = nullptr;             // [0] dt, [1] h_per_v_sig, [2] dt_force_min, [3..5] energy
+    unsigned long long * d_err = nullptr;  // [0] newton non-converged, [1] list overflow
+    Counters * d_cnt = nullptr;
+    int * d_group_counter = nullptr;
+    double dt = 0.0, hpvs = 0.0;
+    bool first_pre = true;
+    unsigned long long nonconverged_total = 0;
+
+    double * scratch_r = nullptr, * scratch_m = nullptr; int pre_grid = 0;
+
+    void * d_aos = nullptr; size_t d_aos_bytes = 0;
+    void * h_stage = nullptr; size_t h_stage_bytes = 0;
+
+    bool counters_on = false, timers_on = false;
+    sphb_counters last_counters{};
+    cudaEvent_t ev[2 * SPHB_T_COUNT] = {};
+    float ms[SPHB_T_COUNT] = {};
+    bool ev_used[SPHB_T_COUNT] = {};
+    uint64_t launches = 0;
+
+    // multi-GPU
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr; bool own_comm = false;
+    int slice_groups = 0;                  // groups of 32 particles per rank
+
+    std::string err;
+};
+
+namespace {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    c->err = std::string(#call) + ": " + cudaGetErrorString(e_); return 1; } } while (0)
+#define CKN(call) do { int e_ = (call); if (e_ != 0) { \
+    c->err = std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(e_) : "nccl error"); return 1; } } while (0)
+#define LAUNCH_CHECK() do { ++c->launches; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { \
+    c->err = std::string("kernel launch: ") + cudaGetErrorString(e_); return 1; } } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+size_t rec_size(int dim) { return (size_t)(4 * dim + 12) * 8 + 16; }
+
+struct Timer {
+    sphb_ctx * c; int k;
+    Timer(sphb_ctx * c_, int k_) : c(c_), k(k_) { if (c->timers_on) cudaEventRecord(c->ev[2 * k], c->stream); }
+    ~Timer() { if (c->timers_on) { cudaEventRecord(c->ev[2 * k + 1], c->stream); c->ev_used[k] = true; } }
+};
+
+template <class T> int dev_alloc(sphb_ctx * c, T ** p, size_t count, std::vector<void *> & bag)
+{
+    void * q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    bag.push_back(q);
+    *p = static_cast<T *>(q);
+    return 0;
+}
+
+void free_bag(std::vector<void *> & bag) { for (void * q : bag) cudaFree(q); bag.clear(); }
+
+// the permuted double / int arrays of a PSoA, in a fixed order
+void list_arrays(sphb_ctx * c, PSoA & s, std::vector<double **> & d, std::vector<int **> & i)
+{
+    const int D = c->dim;
+    for (int k = 0; k < D; ++k) d.push_back(&s.pos[k]);
+    for (int k = 0; k < D; ++k) d.push_back(&s.vel[k]);
+    for (int k = 0; k < D; ++k) d.push_back(&s.vel_p[k]);
+    for (int k = 0; k < D; ++k) d.push_back(&s.acc[k]);
+    double ** sc[] = {&s.mass, &s.dens, &s.pres, &s.ene, &s.ene_p, &s.dene, &s.sml, &s.sound, &s.balsara, &s.alpha, &s.gradh, &s.phi};
+    for (auto q : sc) d.push_back(q);
+    if (c->P.sph_type == T_GSPH) {
+        for (int k = 0; k < D; ++k) d.push_back(&s.grad_d[k]);
+        for (int k = 0; k < D; ++k) d.push_back(&s.grad_p[k]);
+        for (int v = 0; v < D; ++v) for (int k = 0; k < D; ++k) d.push_back(&s.grad_v[v][k]);
+    }
+    i.push_back(&s.pid); i.push_back(&s.neighbor); i.push_back(&s.orig);
+}
+
+int alloc_particles(sphb_ctx * c, int n)
+{
+    free_bag(c->allocs);
+    c->cur = PSoA{}; c->alt = PSoA{};
+    c->n = n;
+    const int groups = cdiv(n, 32);
+    c->slice_groups = cdiv(groups, c->world);
+    c->n_pad = c->slice_groups * c->world * 32;
+    const size_t np = (size_t)c->n_pad;
+
+    for (int side = 0; side < 2; ++side) {
+        PSoA & s = side == 0 ? c->cur : c->alt;
+        std::vector<double **> d; std::vector<int **> iv;
+        list_arrays(c, s, d, iv);
+        c->n_darr = (int)d.size(); c->n_iarr = (int)iv.size();
+        double * pool = nullptr; int * ipool = nullptr;
+        if (dev_alloc(c, &pool, np * d.size(), c->allocs)) return 1;
+        if (dev_alloc(c, &ipool, np * iv.size(), c->allocs)) return 1;
+        CK(cudaMemsetAsync(pool, 0, np * d.size() * sizeof(double), c->stream));
+        CK(cudaMemsetAsync(ipool, 0, np * iv.size() * sizeof(int), c->stream));
+        std::vector<double *> hp(d.size()); std::vector<int *> hi(iv.size());
+        for (size_t k = 0; k < d.size(); ++k) { *d[k] = pool + k * np; hp[k] = *d[k]; }
+        for (size_t k = 0; k < iv.size(); ++k) { *iv[k] = ipool + k * np; hi[k] = *iv[k]; }
+        double ** dp = nullptr; int ** ip = nullptr;
+        if (dev_alloc(c, &dp, d.size(), c->allocs)) return 1;
+        if (dev_alloc(c, &ip, iv.size(), c->allocs)) return 1;
+        CK(cudaMemcpyAsync(dp, hp.data(), hp.size() * sizeof(double *), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(ip, hi.data(), hi.size() * sizeof(int *), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));     // hp / hi go out of scope
+        if (side == 0) { c->d_ptr_cur = dp; c->d_iptr_cur = ip; } else { c->d_ptr_alt = dp; c->d_iptr_alt = ip; }
+    }
+    if (dev_alloc(c, &c->keys, np, c->allocs) || dev_alloc(c, &c->keys_alt, np, c->allocs) ||
+        dev_alloc(c, &c->idx, np, c->allocs) || dev_alloc(c, &c->idx_alt, np, c->allocs)) return 1;
+    c->cub_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, c->cub_tmp_bytes, c->keys, c->keys_alt, c->idx, c->idx_alt, n, 0, 64, c->stream);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int *)nullptr, (int *)nullptr, 5 * n + 2, c->stream);
+    c->cub_tmp_bytes = std::max(c->cub_tmp_bytes, scan_bytes) + 256;
+    { char * t = nullptr; if (dev_alloc(c, &t, c->cub_tmp_bytes, c->allocs)) return 1; c->cub_tmp = t; }
+    c->bbox_blocks = std::min(cdiv(n, 256), 4 * c->sm_count);
+    if (dev_alloc(c, &c->d_bbox_part, (size_t)c->bbox_blocks * 6, c->allocs)) return 1;
+
+    // Newton scratch: one r (and m) column set per resident warp of the persistent pre kernel
+    c->pre_grid = std::min(cdiv(groups, 4), c->sm_count * 4);
+    const size_t slots = (size_t)c->pre_grid * 4;
+    if (dev_alloc(c, &c->scratch_r, slots * c->P.list_cap * 32, c->allocs)) return 1;
+    if (c->P.sph_type != T_DISPH) { if (dev_alloc(c, &c->scratch_m, slots * c->P.list_cap * 32, c->allocs)) return 1; }
+    else c->scratch_m = nullptr;
+
+    c->d_aos_bytes = (size_t)n * rec_size(c->dim);
+    { char * t = nullptr; if (dev_alloc(c, &t, c->d_aos_bytes, c->allocs)) return 1; c->d_aos = t; }
+    c->tree_valid = false;
+    c->first_pre = true;
+    return 0;
+}
+
+int alloc_nodes(sphb_ctx * c, int cap, int keep)
+{
+    // (re)allocate node arrays with capacity `cap`, preserving the first `keep` BFS nodes
+    TreeBuild old = c->tb;
+    std::vector<void *> old_bag;
+    old_bag.swap(c->node_allocs);
+    TreeBuild & t = c->tb;
+    t = TreeBuild{};
+    int ** ia[] = {&t.first, &t.count, &t.level, &t.parent, &t.child0, &t.nchild, &t.size, &t.dfs};
+    int * const oi[] = {old.first, old.count, old.level, old.parent, old.child0, old.nchild, old.size, old.dfs};
+    for (int k = 0; k < 8; ++k) {
+        if (dev_alloc(c, ia[k], cap, c->node_allocs)) return 1;
+        if (keep) CK(cudaMemcpyAsync(*ia[k], oi[k], (size_t)keep * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    for (int d = 0; d < c->dim; ++d) {
+        if (dev_alloc(c, &t.center[d], cap, c->node_allocs)) return 1;
+        if (keep) CK(cudaMemcpyAsync(t.center[d], old.center[d], (size_t)keep * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (dev_alloc(c, &t.mpos[d], cap, c->node_allocs)) return 1;
+    }
+    if (dev_alloc(c, &t.msum, cap, c->node_allocs)) return 1;
+    if (dev_alloc(c, &c->lvl_tmp, cap, c->node_allocs) || dev_alloc(c, &c->lvl_offs, cap, c->node_allocs)) return 1;
+    TreeDev & o = c->td;
+    if (dev_alloc(c, &o.meta, cap, c->node_allocs) || dev_alloc(c, &o.geo, cap, c->node_allocs) ||
+        dev_alloc(c, &o.com, cap, c->node_allocs) || dev_alloc(c, &o.ksize, cap, c->node_allocs) ||
+        dev_alloc(c, &o.parent, cap, c->node_allocs)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    free_bag(old_bag);
+    c->node_cap = cap;
+    return 0;
+}
+
+// ---- AoS <-> SoA --------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_unpack(const char * __restrict__ aos, size_t stride, PSoA s, int n, uint32_t mask, int first)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = first ? i : s.orig[i];
+    const double * r = reinterpret_cast<const double *>(aos + (size_t)k * stride);
+    if (first) s.orig[i] = i;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        if (mask & SPHB_F_POS)   s.pos[d][i]   = r[d];
+        if (mask & SPHB_F_VEL)   s.vel[d][i]   = r[DIM + d];
+        if (mask & SPHB_F_VEL_P) s.vel_p[d][i] = r[2 * DIM + d];
+        if (mask & SPHB_F_ACC)   s.acc[d][i]   = r[3 * DIM + d];
+    }
+    const double * q = r + 4 * DIM;
+    if (mask & SPHB_F_MASS)    s.mass[i]    = q[0];
+    if (mask & SPHB_F_DENS)    s.dens[i]    = q[1];
+    if (mask & SPHB_F_PRES)    s.pres[i]    = q[2];
+    if (mask & SPHB_F_ENE)     s.ene[i]     = q[3];
+    if (mask & SPHB_F_ENE_P)   s.ene_p[i]   = q[4];
+    if (mask & SPHB_F_DENE)    s.dene[i]    = q[5];
+    if (mask & SPHB_F_SML)     s.sml[i]     = q[6];
+    if (mask & SPHB_F_SOUND)   s.sound[i]   = q[7];
+    if (mask & SPHB_F_BALSARA) s.balsara[i] = q[8];
+    if (mask & SPHB_F_ALPHA)   s.alpha[i]   = q[9];
+    if (mask & SPHB_F_GRADH)   s.gradh[i]   = q[10];
+    if (mask & SPHB_F_PHI)     s.phi[i]     = q[11];
+    const int * iq = reinterpret_cast<const int *>(q + 12);
+    if (mask & SPHB_F_ID)       s.pid[i]      = iq[0];
+    if (mask & SPHB_F_NEIGHBOR) s.neighbor[i] = iq[1];
+}
+
+template <int DIM>
+__global__ void k_pack(char * __restrict__ aos, size_t stride, PSoA s, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = s.orig[i];
+    double * r = reinterpret_cast<double *>(aos + (size_t)k * stride);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        r[d] = s.pos[d][i]; r[DIM + d] = s.vel[d][i]; r[2 * DIM + d] = s.vel_p[d][i]; r[3 * DIM + d] = s.acc[d][i];
+    }
+    double * q = r + 4 * DIM;
+    q[0] = s.mass[i]; q[1] = s.dens[i]; q[2] = s.pres[i]; q[3] = s.ene[i]; q[4] = s.ene_p[i]; q[5] = s.dene[i];
+    q[6] = s.sml[i]; q[7] = s.sound[i]; q[8] = s.balsara[i]; q[9] = s.alpha[i]; q[10] = s.gradh[i]; q[11] = s.phi[i];
+    int * iq = reinterpret_cast<int *>(q + 12);
+    iq[0] = s.pid[i]; iq[1] = s.neighbor[i];
+    q[13] = 0.0;       // SPHParticle::next: tree scratch in the reference, null here
+}
+
+__global__ void k_scatter_by_orig(const double * __restrict__ src, const int * __restrict__ orig, double * __restrict__ dst, int n, int ncomp, int comp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[(size_t)orig[i] * ncomp + comp] = src[i];
+}
+__global__ void k_gather_by_orig(const double * __restrict__ src, const int * __restrict__ orig, double * __restrict__ dst, int n, int ncomp, int comp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[(size_t)orig[i] * ncomp + comp];
+}
+__global__ void k_set_scalars(double * s, double dt, double hpvs, int which)
+{
+    if (which & 1) s[0] = dt;
+    if (which & 2) s[1] = hpvs;
+}
+
+// ---- tree ---------------------------------------------------------------------------------------------
+template <int DIM> int make_tree_t(sphb_ctx * c)
+{
+    Timer tm(c, SPHB_T_TREE);
+    const int n = c->n;
+    const int B = 256;
+    if (!c->P.periodic) {
+        k_bbox_partial<DIM><<<c->bbox_blocks, B, 0, c->stream>>>(c->cur, n, c->d_bbox_part); LAUNCH_CHECK();
+        k_bbox_final<DIM><<<1, 32, 0, c->stream>>>(c->d_bbox_part, c->bbox_blocks, c->d_root); LAUNCH_CHECK();
+    }
+    k_keys<DIM><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, n, c->d_root, c->P.key_levels, c->keys, c->idx); LAUNCH_CHECK();
+    size_t tmp = c->cub_tmp_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_alt, c->idx, c->idx_alt, n, 0,
+                                       std::min(64, c->P.key_levels * DIM), c->stream));
+    ++c->launches;
+    k_permute<<<cdiv(n, B), B, 0, c->stream>>>(c->d_ptr_cur, c->d_ptr_alt, c->n_darr, c->d_iptr_cur, c->d_iptr_alt, c->n_iarr, c->idx_alt, n);
+    LAUNCH_CHECK();
+    std::swap(c->cur, c->alt);
+    std::swap(c->d_ptr_cur, c->d_ptr_alt);
+    std::swap(c->d_iptr_cur, c->d_iptr_alt);
+    const unsigned long long * keys = c->keys_alt;
+
+    if (c->node_cap == 0) { if (alloc_nodes(c, std::max(1024, n / 2 + 64), 0)) return 1; }
+    const int max_level_eff = std::min(c->P.max_level, c->P.key_levels);
+    const long long node_limit = 5LL * n + 1;          // BHTree::resize: 5 N nodes + the root (src/bhtree.cpp:46)
+    k_root_init<<<1, 32, 0, c->stream>>>(c->tb, n, c->d_root); LAUNCH_CHECK();
+    c->levels.clear();
+    int lb = 0, le = 1;
+    while (le > lb) {
+        c->levels.push_back({lb, le});
+        const int w = le - lb;
+        k_level_count<DIM><<<cdiv(w, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_tmp);
+        LAUNCH_CHECK();
+        size_t tb = c->cub_tmp_bytes;
+        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->lvl_tmp, c->lvl_offs, w, c->stream));
+        ++c->launches;
+        int last_off = 0, last_cnt = 0;
+        CK(cudaMemcpyAsync(&last_off, c->lvl_offs + (w - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&last_cnt, c->lvl_tmp + (w - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const int total = last_off + last_cnt;
+        if ((long long)le + total > node_limit) { c->err = "There is no free node."; return 1; }    // src/bhtree.cpp:179-181
+        if (le + total > c->node_cap) {
+            const int ncap = (int)std::min<long long>(node_limit, std::max<long long>(2LL * c->node_cap, (long long)le + total + 1024));
+            if (alloc_nodes(c, ncap, le)) return 1;
+        }
+        k_level_emit<DIM><<<cdiv(w, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_offs, c->d_root);
+        LAUNCH_CHECK();
+        lb = le; le += total;
+    }
+    const int n_nodes = lb;
+    for (int l = (int)c->levels.size() - 1; l >= 0; --l) {
+        const int a = c->levels[l].first, b = c->levels[l].second;
+        k_level_up<DIM><<<cdiv(b - a, B), B, 0, c->stream>>>(c->tb, c->cur, a, b); LAUNCH_CHECK();
+    }
+    for (size_t l = 0; l < c->levels.size(); ++l) {
+        const int a = c->levels[l].first, b = c->levels[l].second;
+        k_level_dfs<<<cdiv(b - a, B), B, 0, c->stream>>>(c->tb, a, b); LAUNCH_CHECK();
+    }
+    c->td.n_nodes = n_nodes;
+    k_tree_scatter<DIM><<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, c->td, n_nodes, c->d_root); LAUNCH_CHECK();
+    c->tree_valid = true;
+    c->last_counters.tree_nodes = (uint64_t)n_nodes;
+    return 0;
+}
+
+int set_kernel(sphb_ctx * c)
+{
+    CK(cudaMemsetAsync(c->td.ksize, 0, (size_t)c->td.n_nodes * sizeof(double), c->stream));
+    k_set_kernel<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td, c->cur.sml); LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- multi-GPU exchange: every rank owns slice_groups*32 consecutive particles of the sorted order
+int gather_d(sphb_ctx * c, double * a)
+{
+    const size_t cnt = (size_t)c->slice_groups * 32;
+    CKN(g_nccl.AllGather(a + cnt * c->rank, a, cnt, ncclFloat64, c->comm, c->stream));
+    return 0;
+}
+int gather_i(sphb_ctx * c, int * a)
+{
+    const size_t cnt = (size_t)c->slice_groups * 32;
+    CKN(g_nccl.AllGather(a + cnt * c->rank, a, cnt, ncclInt32, c->comm, c->stream));
+    return 0;
+}
+
+// ---- stages --------------------------------------------------------------------------------------------
+// A rank computes groups [g0, g0 + ng) of the sorted order; kernels take a particle-offset view.
+struct Slice { int first_particle, n_local; };
+Slice my_slice(sphb_ctx * c)
+{
+    if (c->world == 1) return {0, c->n};
+    const long long f = (long long)c->rank * c->slice_groups * 32;
+    const long long l = std::min<long long>(c->n, f + (long long)c->slice_groups * 32);
+    return {(int)std::min<long long>(f, c->n), (int)std::max<long long>(0, l - f)};
+}
+
+} // namespace
+
+namespace {
+
+template <int DIM, int KT, int SPH> int pre_t(sphb_ctx * c)
+{
+    Timer tm(c, SPHB_T_PRE);
+    const Slice s = my_slice(c);
+    const int g0 = s.first_particle / 32;
+    const int ng = cdiv(s.n_local, 32);
+    if (c->first_pre) {
+        // initial_smoothing needs every particle's density before the main pass: all ranks do all
+        // particles (first call only)
+        k_initial_smoothing<DIM, KT><<<cdiv(cdiv(c->n, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n); LAUNCH_CHECK();
+        c->first_pre = false;
+    }
+    k_set_scalars<<<1, 1, 0, c->stream>>>(c->d_scal, 0.0, DBL_MAX, 2); LAUNCH_CHECK();
+    // group counter starts at g0; the kernel stops at g0 + ng
+    CK(cudaMemcpyAsync(c->d_group_counter, &g0, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (ng > 0) {
+        const int grid = std::min(c->pre_grid, cdiv(ng, 4));
+        k_pre_interaction<DIM, KT, SPH><<<grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n, g0 + ng, c->d_group_counter,
+            c->scratch_r, c->scratch_m, c->d_scal + 0, c->d_scal + 1, c->d_err, c->counters_on ? c->d_cnt : nullptr);
+        LAUNCH_CHECK();
+    }
+    if (c->world > 1) {
+        Timer tx(c, SPHB_T_EXCHANGE);
+        PSoA & p = c->cur;
+        CKN(g_nccl.GroupStart());
+        double * arr[] = {p.sml, p.dens, p.pres, p.gradh, p.balsara, p.alpha};
+        for (double * a : arr) if (gather_d(c, a)) return 1;
+        if (gather_i(c, p.neighbor)) return 1;
+        if (SPH == T_GSPH) {
+            for (int k = 0; k < DIM; ++k) { if (gather_d(c, p.grad_d[k]) || gather_d(c, p.grad_p[k])) return 1; }
+            for (int v = 0; v < DIM; ++v) for (int k = 0; k < DIM; ++k) if (gather_d(c, p.grad_v[v][k])) return 1;
+        }
+        CKN(g_nccl.AllReduce(c->d_scal + 1, c->d_scal + 1, 1, ncclFloat64, ncclMin, c->comm, c->stream));
+        CKN(g_nccl.GroupEnd());
+    }
+    return set_kernel(c);
+}
+
+template <int DIM> int pre_d(sphb_ctx * c)
+{
+    const int kt = c->P.kernel, st = c->P.sph_type;
+#define SPHB_PRE(K, S) if (kt == K && st == S) return pre_t<DIM, K, S>(c);
+    SPHB_PRE(K_CUBIC, T_SSPH) SPHB_PRE(K_CUBIC, T_DISPH) SPHB_PRE(K_CUBIC, T_GSPH)
+    if (DIM > 1) {
+        constexpr int D2 = DIM > 1 ? DIM : 2;
+        if (kt == K_WENDLAND && st == T_SSPH) return pre_t<D2, K_WENDLAND, T_SSPH>(c);
+        if (kt == K_WENDLAND && st == T_DISPH) return pre_t<D2, K_WENDLAND, T_DISPH>(c);
+        if (kt == K_WENDLAND && st == T_GSPH) return pre_t<D2, K_WENDLAND, T_GSPH>(c);
+    }
+#undef SPHB_PRE
+    c->err = "unsupported kernel / SPH type"; return 1;
+}
+
+template <int DIM, int KT, int SPH> int force_t(sphb_ctx * c)
+{
+    Timer tm(c, SPHB_T_FLUID);
+    const Slice s = my_slice(c);
+    if (s.n_local > 0) {
+        k_fluid_force<DIM, KT, SPH><<<cdiv(cdiv(s.n_local, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n,
+            s.first_particle, s.first_particle + s.n_local, c->d_scal + 0, c->counters_on ? c->d_cnt : nullptr);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+template <int DIM> int force_d(sphb_ctx * c)
+{
+    const int kt = c->P.kernel, st = c->P.sph_type;
+    if (kt == K_CUBIC && st == T_SSPH) return force_t<DIM, K_CUBIC, T_SSPH>(c);
+    if (kt == K_CUBIC && st == T_DISPH) return force_t<DIM, K_CUBIC, T_DISPH>(c);
+    if (kt == K_CUBIC && st == T_GSPH) return force_t<DIM, K_CUBIC, T_GSPH>(c);
+    if (DIM > 1) {
+        constexpr int D2 = DIM > 1 ? DIM : 2;
+        if (kt == K_WENDLAND && st == T_SSPH) return force_t<D2, K_WENDLAND, T_SSPH>(c);
+        if (kt == K_WENDLAND && st == T_DISPH) return force_t<D2, K_WENDLAND, T_DISPH>(c);
+        if (kt == K_WENDLAND && st == T_GSPH) return force_t<D2, K_WENDLAND, T_GSPH>(c);
+    }
+    c->err = "unsupported kernel / SPH type"; return 1;
+}
+
+template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
+{
+    Timer tm(c, SPHB_T_GRAVITY);
+    const Slice s = my_slice(c);
+    if (direct) {
+        if (c->world > 1) { c->err = "sphb_gravity_direct is single-GPU only"; return 1; }
+        k_gravity_direct<DIM><<<cdiv(c->n, 128), 128, 0, c->stream>>>(c->cur, c->P, c->n); LAUNCH_CHECK();
+        return 0;
+    }
+    if (s.n_local > 0) {
+        k_gravity<DIM><<<cdiv(cdiv(s.n_local, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n,
+            s.first_particle, s.first_particle + s.n_local, c->counters_on ? c->d_cnt : nullptr);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// after fluid force (+ gravity): make acc / dene / phi whole again on every rank
+template <int DIM> int exchange_forces(sphb_ctx * c)
+{
+    if (c->world == 1) return 0;
+    Timer tx(c, SPHB_T_EXCHANGE);
+    PSoA & p = c->cur;
+    CKN(g_nccl.GroupStart());
+    for (int d = 0; d < DIM; ++d) if (gather_d(c, p.acc[d])) return 1;
+    if (gather_d(c, p.dene)) return 1;
+    if (c->P.use_gravity && gather_d(c, p.phi)) return 1;
+    CKN(g_nccl.GroupEnd());
+    return 0;
+}
+
+template <int DIM> int timestep_t(sphb_ctx * c)
+{
+    Timer tm(c, SPHB_T_TIMESTEP);
+    // the force minimum is taken over the rank's slice and all-reduced (min)
+    const Slice s = my_slice(c);
+    const double big = DBL_MAX;
+    CK(cudaMemcpyAsync(c->d_scal + 2, &big, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (s.n_local > 0) {
+        const int grid = std::min(cdiv(s.n_local, 256), 4 * c->sm_count);
+        k_timestep_partial<DIM><<<grid, 256, 0, c->stream>>>(c->cur, s.first_particle, s.first_particle + s.n_local, c->P.cfl_force, c->d_scal + 2);
+        LAUNCH_CHECK();
+    }
+    if (c->world > 1) CKN(g_nccl.AllReduce(c->d_scal + 2, c->d_scal + 2, 1, ncclFloat64, ncclMin, c->comm, c->stream));
+    k_timestep_final<<<1, 1, 0, c->stream>>>(c->d_scal + 2, c->d_scal + 1, c->P.cfl_sound, c->d_scal + 0); LAUNCH_CHECK();
+    return 0;
+}
+
+template <int DIM> int predict_t(sphb_ctx * c)
+{
+    Timer tm(c, SPHB_T_PREDICT);
+    k_predict<DIM><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n, c->d_scal + 0); LAUNCH_CHECK();
+    c->tree_valid = false;
+    return 0;
+}
+template <int DIM> int correct_t(sphb_ctx * c)
+{
+    Timer tm(c, SPHB_T_CORRECT);
+    k_correct<DIM><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n, c->d_scal + 0); LAUNCH_CHECK();
+    return 0;
+}
+
+#define DIM_SWITCH(c, EXPR1, EXPR2, EXPR3) ((c)->dim == 1 ? (EXPR1) : (c)->dim == 2 ? (EXPR2) : (EXPR3))
+
+int make_tree(sphb_ctx * c) { return DIM_SWITCH(c, make_tree_t<1>(c), make_tree_t<2>(c), make_tree_t<3>(c)); }
+int pre(sphb_ctx * c) { return DIM_SWITCH(c, pre_d<1>(c), pre_d<2>(c), pre_d<3>(c)); }
+int force(sphb_ctx * c) { return DIM_SWITCH(c, force_d<1>(c), force_d<2>(c), force_d<3>(c)); }
+int gravity(sphb_ctx * c, bool direct) { return DIM_SWITCH(c, gravity_t<1>(c, direct), gravity_t<2>(c, direct), gravity_t<3>(c, direct)); }
+int exchange(sphb_ctx * c) { return DIM_SWITCH(c, exchange_forces<1>(c), exchange_forces<2>(c), exchange_forces<3>(c)); }
+int timestep(sphb_ctx * c) { return DIM_SWITCH(c, timestep_t<1>(c), timestep_t<2>(c), timestep_t<3>(c)); }
+int predict(sphb_ctx * c) { return DIM_SWITCH(c, predict_t<1>(c), predict_t<2>(c), predict_t<3>(c)); }
+int correct(sphb_ctx * c) { return DIM_SWITCH(c, correct_t<1>(c), correct_t<2>(c), correct_t<3>(c)); }
+
+// copy dt, h_per_v_sig and the error counters to the host; turn device-side errors into a status
+int sync_scalars(sphb_ctx * c)
+{
+    double s[2]; unsigned long long e[2];
+    CK(cudaMemcpyAsync(s, c->d_scal, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(e, c->d_err, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->dt = s[0]; c->hpvs = s[1];
+    c->nonconverged_total = e[0];
+    if (e[1]) {
+        c->err = "neighbor list overflow: a particle has more than neighborNumber*20 candidates (include/defines.hpp:29)";
+        CK(cudaMemsetAsync(c->d_err + 1, 0, sizeof(unsigned long long), c->stream));
+        return 1;
+    }
+    if (c->timers_on) {
+        for (int k = 0; k < SPHB_T_COUNT; ++k) if (c->ev_used[k]) cudaEventElapsedTime(&c->ms[k], c->ev[2 * k], c->ev[2 * k + 1]);
+    }
+    return 0;
+}
+
+int require_tree(sphb_ctx * c)
+{
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->tree_valid) { c->err = "tree is not made for the current positions (call sphb_make_tree)"; return 1; }
+    return 0;
+}
+
+} // namespace
+
+// =====================================================================================================
+extern "C" {
+
+size_t sphb_sizeof_particle(int dim) { return rec_size(dim); }
+
+int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
+{
+    if (!hp || !out || dim < 1 || dim > 3) { g_create_error = "bad arguments"; return 1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_error = "no CUDA device (libsphb has no CPU fallback)"; return 1; }
+    if (device < 0 || device >= ndev) { g_create_error = "bad device ordinal"; return 1; }
+    if (hp->kernel == SPHB_WENDLAND && dim == 1) { g_create_error = "Wendland C4 is not defined for DIM == 1 (wendland_kernel.hpp:25-28)"; return 1; }
+    if (hp->kernel != SPHB_CUBIC_SPLINE && hp->kernel != SPHB_WENDLAND) { g_create_error = "kernel is unknown."; return 1; }   // src/simulation.cpp:19
+    if (hp->sph_type < 0 || hp->sph_type > 2) { g_create_error = "Unknown SPH type"; return 1; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "cudaSetDevice failed"; return 1; }
+    sphb_ctx * c = new sphb_ctx;
+    c->dim = dim; c->device = device; c->hp = *hp;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->sm_count = prop.multiProcessorCount;
+    DevParams & P = c->P;
+    P.sph_type = hp->sph_type; P.kernel = hp->kernel;
+    P.cfl_sound = hp->cfl_sound; P.cfl_force = hp->cfl_force;
+    P.av_alpha = hp->av_alpha; P.use_balsara = hp->use_balsara_switch; P.use_tdav = hp->use_time_dependent_av;
+    P.alpha_max = hp->alpha_max; P.alpha_min = hp->alpha_min; P.epsilon_av = hp->epsilon_av;
+    P.use_ac = hp->use_ac; P.alpha_ac = hp->alpha_ac;
+    P.max_level = hp->max_tree_level; P.leaf_num = hp->leaf_particle_num; P.ngb = hp->neighbor_number;
+    P.iterative = hp->iterative_sml; P.gamma = hp->gamma;
+    P.periodic = hp->periodic; P.use_gravity = hp->use_gravity;
+    for (int d = 0; d < 3; ++d) {
+        P.rmax[d] = d < dim ? hp->range_max[d] : 0.0; P.rmin[d] = d < dim ? hp->range_min[d] : 0.0;
+        P.range[d] = P.rmax[d] - P.rmin[d];
+    }
+    P.G = hp->G; P.theta = hp->theta; P.theta2 = hp->theta * hp->theta;
+    P.gsph2 = hp->gsph_2nd_order;
+    P.kernel_ratio = hp->iterative_sml ? 1.2 : 1.0;
+    P.key_levels = std::max(1, std::min(hp->max_tree_level, 63 / dim));
+    P.list_cap = hp->neighbor_number * 20;
+    cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    void * q = nullptr;
+    cudaMalloc(&q, 4 * sizeof(double)); c->d_root = (double *)q;
+    cudaMalloc(&q, 8 * sizeof(double)); c->d_scal = (double *)q;
+    cudaMalloc(&q, 2 * sizeof(unsigned long long)); c->d_err = (unsigned long long *)q;
+    cudaMalloc(&q, sizeof(Counters)); c->d_cnt = (Counters *)q;
+    cudaMalloc(&q, sizeof(int)); c->d_group_counter = (int *)q;
+    cudaMemset(c->d_scal, 0, 8 * sizeof(double));
+    cudaMemset(c->d_err, 0, 2 * sizeof(unsigned long long));
+    cudaMemset(c->d_cnt, 0, sizeof(Counters));
+    if (P.periodic) {
+        // BHTree::initialize, src/bhtree.cpp:19-31
+        double root[4] = {0, 0, 0, 0};
+        double l = 0.0;
+        for (int d = 0; d < dim; ++d) {
+            root[d] = (P.rmax[d] + P.rmin[d]) * 0.5;
+            if (l < P.range[d]) l = P.range[d];
+        }
+        root[3] = l;
+        cudaMemcpy(c->d_root, root, sizeof(root), cudaMemcpyHostToDevice);
+    }
+    for (int k = 0; k < 2 * SPHB_T_COUNT; ++k) cudaEventCreate(&c->ev[k]);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
+    *out = c;
+    return 0;
+}
+
+void sphb_destroy(sphb_ctx * c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    free_bag(c->allocs); free_bag(c->node_allocs);
+    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char * sphb_last_error(const sphb_ctx * c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int sphb_set_stream(sphb_ctx * c, void * s)
+{
+    cudaStreamSynchronize(c->stream);
+    c->stream = (cudaStream_t)s;      // the context's own stream is kept alive until destroy only if never replaced
+    return 0;
+}
+int sphb_synchronize(sphb_ctx * c) { CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return 0; }
+int sphb_dim(const sphb_ctx * c) { return c->dim; }
+int sphb_particle_num(const sphb_ctx * c) { return c->n; }
+
+int sphb_nccl_unique_id(void * out128)
+{
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_error = err; return 1; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return 1; }
+    std::memcpy(out128, &id, sizeof(id));
+    return 0;
+}
+
+int sphb_set_distributed(sphb_ctx * c, int rank, int world, void * nccl_comm)
+{
+    if (world < 1 || rank < 0 || rank >= world) { c->err = "bad rank / world"; return 1; }
+    if (c->n) { c->err = "sphb_set_distributed must precede the first upload"; return 1; }
+    if (world > 1) {
+        if (!g_nccl.load(c->err)) return 1;
+        if (!nccl_comm) { c->err = "nccl communicator required"; return 1; }
+        c->comm = (ncclComm_t)nccl_comm; c->own_comm = false;
+    }
+    c->rank = rank; c->world = world;
+    return 0;
+}
+
+int sphb_set_distributed_id(sphb_ctx * c, int rank, int world, const void * unique_id128)
+{
+    if (world < 1 || rank < 0 || rank >= world) { c->err = "bad rank / world"; return 1; }
+    if (c->n) { c->err = "sphb_set_distributed_id must precede the first upload"; return 1; }
+    if (world > 1) {
+        if (!g_nccl.load(c->err)) return 1;
+        CK(cudaSetDevice(c->device));
+        ncclUniqueId id;
+        std::memcpy(&id, unique_id128, sizeof(id));
+        ncclComm_t comm = nullptr;
+        CKN(g_nccl.CommInitRank(&comm, world, id, rank));
+        c->comm = comm; c->own_comm = true;
+    }
+    c->rank = rank; c->world = world;
+    return 0;
+}
+
+// ---- state transfer -----------------------------------------------------------------------------------
+int sphb_upload_aos(sphb_ctx * c, const void * particles, int n, size_t stride, uint32_t mask)
+{
+    CK(cudaSetDevice(c->device));
+    const size_t rec = rec_size(c->dim);
+    if (!particles || n <= 0 || stride < rec) { c->err = "bad upload arguments"; return 1; }
+    const bool first = (n != c->n);
+    if (first) {
+        if ((mask & SPHB_F_ALL) != SPHB_F_ALL) { c->err = "the first upload must use SPHB_F_ALL"; return 1; }
+        if (alloc_particles(c, n)) return 1;
+    }
+    if (stride == rec) CK(cudaMemcpyAsync(c->d_aos, particles, rec * n, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemcpy2DAsync(c->d_aos, rec, particles, stride, rec, n, cudaMemcpyHostToDevice, c->stream));
+    switch (c->dim) {
+    case 1: k_unpack<1><<<cdiv(n, 256), 256, 0, c->stream>>>((const char *)c->d_aos, rec, c->cur, n, mask, first); break;
+    case 2: k_unpack<2><<<cdiv(n, 256), 256, 0, c->stream>>>((const char *)c->d_aos, rec, c->cur, n, mask, first); break;
+    default: k_unpack<3><<<cdiv(n, 256), 256, 0, c->stream>>>((const char *)c->d_aos, rec, c->cur, n, mask, first); break;
+    }
+    LAUNCH_CHECK();
+    if (mask & SPHB_F_POS) c->tree_valid = false;
+    CK(cudaStreamSynchronize(c->stream));        // the caller may reuse its buffer
+    return 0;
+}
+
+int sphb_download_aos(sphb_ctx * c, void * particles, int n, size_t stride, uint32_t mask)
+{
+    CK(cudaSetDevice(c->device));
+    const size_t rec = rec_size(c->dim);
+    if (!particles || n != c->n || stride < rec) { c->err = "bad download arguments"; return 1; }
+    switch (c->dim) {
+    case 1: k_pack<1><<<cdiv(n, 256), 256, 0, c->stream>>>((char *)c->d_aos, rec, c->cur, n); break;
+    case 2: k_pack<2><<<cdiv(n, 256), 256, 0, c->stream>>>((char *)c->d_aos, rec, c->cur, n); break;
+    default: k_pack<3><<<cdiv(n, 256), 256, 0, c->stream>>>((char *)c->d_aos, rec, c->cur, n); break;
+    }
+    LAUNCH_CHECK();
+    if ((mask & SPHB_F_ALL) == SPHB_F_ALL) {
+        if (stride == rec) CK(cudaMemcpyAsync(particles, c->d_aos, rec * n, cudaMemcpyDeviceToHost, c->stream));
+        else CK(cudaMemcpy2DAsync(particles, stride, c->d_aos, rec, rec, n, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    if (c->h_stage_bytes < rec * n) {
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        CK(cudaMallocHost(&c->h_stage, rec * n));
+        c->h_stage_bytes = rec * n;
+    }
+    CK(cudaMemcpyAsync(c->h_stage, c->d_aos, rec * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int D = c->dim;
+    const uint32_t vec_bits[4] = {SPHB_F_POS, SPHB_F_VEL, SPHB_F_VEL_P, SPHB_F_ACC};
+    for (int i = 0; i < n; ++i) {
+        const char * src = (const char *)c->h_stage + (size_t)i * rec;
+        char * dst = (char *)particles + (size_t)i * stride;
+        for (int v = 0; v < 4; ++v) if (mask & vec_bits[v]) std::memcpy(dst + (size_t)v * D * 8, src + (size_t)v * D * 8, (size_t)D * 8);
+        for (int k = 0; k < 12; ++k) if (mask & (SPHB_F_MASS << k)) std::memcpy(dst + (size_t)(4 * D + k) * 8, src + (size_t)(4 * D + k) * 8, 8);
+        if (mask & SPHB_F_ID) std::memcpy(dst + (size_t)(4 * D + 12) * 8, src + (size_t)(4 * D + 12) * 8, 4);
+        if (mask & SPHB_F_NEIGHBOR) std::memcpy(dst + (size_t)(4 * D + 12) * 8 + 4, src + (size_t)(4 * D + 12) * 8 + 4, 4);
+    }
+    return 0;
+}
+
+static double ** vector_array_by_name(sphb_ctx * c, const char * name)
+{
+    if (c->P.sph_type != T_GSPH) { c->err = std::string("additional_vector_array does not have ") + name; return nullptr; }   // src/simulation.cpp:74
+    PSoA & p = c->cur;
+    if (!std::strcmp(name, "grad_density")) return p.grad_d;
+    if (!std::strcmp(name, "grad_pressure")) return p.grad_p;
+    if (!std::strncmp(name, "grad_velocity_", 14)) {
+        const int k = name[14] - '0';
+        if (k >= 0 && k < c->dim && name[15] == 0) return p.grad_v[k];
+    }
+    c->err = std::string("additional_vector_array does not have ") + name;
+    return nullptr;
+}
+
+int sphb_get_vector_array(sphb_ctx * c, const char * name, double * out)
+{
+    CK(cudaSetDevice(c->device));
+    double ** a = vector_array_by_name(c, name);
+    if (!a) return 1;
+    double * tmp = (double *)c->d_aos;      // n*dim doubles fit in the AoS staging buffer
+    for (int k = 0; k < c->dim; ++k) { k_scatter_by_orig<<<cdiv(c->n, 256), 256, 0, c->stream>>>(a[k], c->cur.orig, tmp, c->n, c->dim, k); LAUNCH_CHECK(); }
+    CK(cudaMemcpyAsync(out, tmp, (size_t)c->n * c->dim * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sphb_set_vector_array(sphb_ctx * c, const char * name, const double * in)
+{
+    CK(cudaSetDevice(c->device));
+    double ** a = vector_array_by_name(c, name);
+    if (!a) return 1;
+    double * tmp = (double *)c->d_aos;
+    CK(cudaMemcpyAsync(tmp, in, (size_t)c->n * c->dim * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k < c->dim; ++k) { k_gather_by_orig<<<cdiv(c->n, 256), 256, 0, c->stream>>>(tmp, c->cur.orig, a[k], c->n, c->dim, k); LAUNCH_CHECK(); }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int sphb_set_dt(sphb_ctx * c, double dt)
+{
+    CK(cudaSetDevice(c->device));
+    c->dt = dt;
+    k_set_scalars<<<1, 1, 0, c->stream>>>(c->d_scal, dt, 0.0, 1); LAUNCH_CHECK();
+    return 0;
+}
+int sphb_get_dt(sphb_ctx * c, double * dt) { CK(cudaSetDevice(c->device)); if (sync_scalars(c)) return 1; *dt = c->dt; return 0; }
+int sphb_set_h_per_v_sig(sphb_ctx * c, double v)
+{
+    CK(cudaSetDevice(c->device));
+    c->hpvs = v;
+    k_set_scalars<<<1, 1, 0, c->stream>>>(c->d_scal, 0.0, v, 2); LAUNCH_CHECK();
+    return 0;
+}
+int sphb_get_h_per_v_sig(sphb_ctx * c, double * v) { CK(cudaSetDevice(c->device)); if (sync_scalars(c)) return 1; *v = c->hpvs; return 0; }
+
+// ---- the hot path -----------------------------------------------------------------------------------------
+int sphb_init_state(sphb_ctx * c)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    k_init_state<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n); LAUNCH_CHECK();
+    return 0;
+}
+
+int sphb_make_tree(sphb_ctx * c)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    return make_tree(c);
+}
+
+int sphb_pre_interaction(sphb_ctx * c)
+{
+    CK(cudaSetDevice(c->device));
+    if (require_tree(c)) return 1;
+    if (pre(c)) return 1;
+    return sync_scalars(c);
+}
+
+int sphb_fluid_force(sphb_ctx * c)
+{
+    CK(cudaSetDevice(c->device));
+    if (require_tree(c)) return 1;
+    if (force(c)) return 1;
+    if (!c->P.use_gravity) { if (exchange(c)) return 1; }
+    return 0;
+}
+
+int sphb_gravity_force(sphb_ctx * c)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->P.use_gravity) return 0;                  // src/gravity_force.cpp:54-56
+    if (require_tree(c)) return 1;
+    if (gravity(c, false)) return 1;
+    return exchange(c);
+}
+
+int sphb_gravity_direct(sphb_ctx * c)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->P.use_gravity) return 0;
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    return gravity(c, true);
+}
+
+int sphb_timestep(sphb_ctx * c, double * dt)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (timestep(c)) return 1;
+    if (sync_scalars(c)) return 1;
+    if (dt) *dt = c->dt;
+    return 0;
+}
+
+int sphb_predict(sphb_ctx * c) { CK(cudaSetDevice(c->device)); if (!c->n) { c->err = "no particles uploaded"; return 1; } return predict(c); }
+int sphb_correct(sphb_ctx * c) { CK(cudaSetDevice(c->device)); if (!c->n) { c->err = "no particles uploaded"; return 1; } return correct(c); }
+
+int sphb_initialize(sphb_ctx * c)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (sphb_init_state(c) || make_tree(c) || pre(c) || force(c)) return 1;
+    if (c->P.use_gravity) { if (gravity(c, false)) return 1; }
+    if (exchange(c)) return 1;
+    return sync_scalars(c);
+}
+
+int sphb_integrate(sphb_ctx * c, double * dt)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (timestep(c) || predict(c) || make_tree(c) || pre(c) || force(c)) return 1;
+    if (c->P.use_gravity) { if (gravity(c, false)) return 1; }
+    if (exchange(c) || correct(c)) return 1;
+    if (sync_scalars(c)) return 1;
+    if (dt) *dt = c->dt;
+    return 0;
+}
+
+int sphb_energy(sphb_ctx * c, double out[3])
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    CK(cudaMemsetAsync(c->d_scal + 3, 0, 3 * sizeof(double), c->stream));
+    const int grid = std::min(cdiv(c->n, 256), 4 * c->sm_count);
+    switch (c->dim) {
+    case 1: k_energy<1><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
+    case 2: k_energy<2><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
+    default: k_energy<3><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
+    }
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(out, c->d_scal + 3, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- test / measurement hooks ---------------------------------------------------------------------------
+int sphb_neighbor_lists(sphb_ctx * c, const double * h, int symmetric, int64_t * offsets, int32_t * ids, int64_t cap_total, int64_t * total)
+{
+    CK(cudaSetDevice(c->device));
+    if (require_tree(c)) return 1;
+    const int n = c->n;
+    if (symmetric) { if (set_kernel(c)) return 1; }
+    std::vector<void *> bag;
+    double * d_h = nullptr; int * d_counts = nullptr; long long * d_offs = nullptr; int * d_ids = nullptr;
+    if (h) {
+        double * d_h_orig = nullptr;
+        if (dev_alloc(c, &d_h_orig, n, bag) || dev_alloc(c, &d_h, n, bag)) { free_bag(bag); return 1; }
+        CK(cudaMemcpyAsync(d_h_orig, h, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        k_gather_by_orig<<<cdiv(n, 256), 256, 0, c->stream>>>(d_h_orig, c->cur.orig, d_h, n, 1, 0); LAUNCH_CHECK();
+    }
+    if (dev_alloc(c, &d_counts, n, bag) || dev_alloc(c, &d_offs, n + 1, bag)) { free_bag(bag); return 1; }
+    const int grid = cdiv(cdiv(n, 32), 4);
+#define NL(D, FILL) k_neighbor_lists<D><<<grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, n, d_h, symmetric, FILL, d_counts, d_offs, d_ids, cap_total)
+    switch (c->dim) { case 1: NL(1, 0); break; case 2: NL(2, 0); break; default: NL(3, 0); break; }
+    LAUNCH_CHECK();
+    std::vector<int> counts(n), orig(n);
+    CK(cudaMemcpyAsync(counts.data(), d_counts, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(orig.data(), c->cur.orig, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    // CSR in the caller's particle order
+    std::vector<long long> cnt_orig(n);
+    for (int s = 0; s < n; ++s) cnt_orig[orig[s]] = counts[s];
+    long long tot = 0;
+    for (int k = 0; k < n; ++k) { offsets[k] = tot; tot += cnt_orig[k]; }
+    offsets[n] = tot;
+    if (total) *total = tot;
+    if (ids && cap_total > 0) {
+        std::vector<long long> offs_sorted(n + 1);
+        for (int s = 0; s < n; ++s) offs_sorted[s] = offsets[orig[s]];
+        offs_sorted[n] = tot;
+        const long long cap = std::min<long long>(cap_total, tot);
+        if (dev_alloc(c, &d_ids, (size_t)std::max<long long>(cap, 1), bag)) { free_bag(bag); return 1; }
+        CK(cudaMemcpyAsync(d_offs, offs_sorted.data(), (size_t)(n + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+        switch (c->dim) { case 1: NL(1, 1); break; case 2: NL(2, 1); break; default: NL(3, 1); break; }
+        LAUNCH_CHECK();
+        CK(cudaMemcpyAsync(ids, d_ids, (size_t)cap * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < n; ++k) {
+            const long long a = std::min<long long>(offsets[k], cap), b = std::min<long long>(offsets[k + 1], cap);
+            std::sort(ids + a, ids + b);
+        }
+    }
+#undef NL
+    CK(cudaStreamSynchronize(c->stream));
+    free_bag(bag);
+    return 0;
+}
+
+int sphb_enable_counters(sphb_ctx * c, int enable)
+{
+    CK(cudaSetDevice(c->device));
+    c->counters_on = enable != 0;
+    CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), c->stream));
+    return 0;
+}
+
+int sphb_get_counters(sphb_ctx * c, sphb_counters * out)
+{
+    CK(cudaSetDevice(c->device));
+    Counters h;
+    CK(cudaMemcpyAsync(&h, c->d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemsetAsync(c->d_cnt, 0, sizeof(Counters), c->stream));
+    sphb_counters & o = c->last_counters;
+    o.n_particles = (uint64_t)c->n;
+    o.newton_evals = h.newton_evals; o.newton_iters = h.newton_iters;
+    o.pre_candidates = h.pre_candidates; o.pre_neighbors = h.pre_neighbors;
+    o.force_pairs = h.force_pairs; o.grav_pp = h.grav_pp; o.grav_pc = h.grav_pc; o.grav_node_visits = h.grav_node_visits;
+    if (c->tree_valid) {
+        std::vector<int4> meta(c->td.n_nodes);
+        CK(cudaMemcpy(meta.data(), c->td.meta, meta.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+        uint64_t leaves = 0;
+        for (auto & m : meta) leaves += m.w ? 1 : 0;
+        o.tree_leaves = leaves; o.tree_nodes = (uint64_t)c->td.n_nodes;
+    }
+    *out = o;
+    return 0;
+}
+
+int sphb_enable_timers(sphb_ctx * c, int enable) { c->timers_on = enable != 0; for (auto & u : c->ev_used) u = false; for (auto & m : c->ms) m = 0.f; return 0; }
+int sphb_get_timers(sphb_ctx * c, float ms[SPHB_T_COUNT])
+{
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < SPHB_T_COUNT; ++k) {
+        if (c->ev_used[k]) cudaEventElapsedTime(&c->ms[k], c->ev[2 * k], c->ev[2 * k + 1]);
+        ms[k] = c->ms[k];
+    }
+    return 0;
+}
+
+uint64_t sphb_launch_count(const sphb_ctx * c) { return c->launches; }
+uint64_t sphb_nonconverged(const sphb_ctx * c) { return c->nonconverged_total; }
+
+void * sphb_host_alloc(size_t bytes) { void * p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p; }
+void sphb_host_free(void * p) { if (p) cudaFreeHost(p); }
+
+int sphb_bench_fp64(int device, double * tflops)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return 1;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double * out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return 1;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    k_fp64_peak<<<blocks, threads>>>(out, 1024);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a);
+        k_fp64_peak<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        best = std::min(best, ms);
+    }
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(out);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+} // extern "C"

@@ -1,0 +1,930 @@
+// sphb_stages.cuh — the per-step stage kernels (sm_100a, FP64):
+//   PreInteraction   src/pre_interaction.cpp:39-283, src/disph/d_pre_interaction.cpp:21-230,
+//                    src/gsph/g_pre_interaction.cpp:27-144
+//   FluidForce       src/fluid_force.cpp:26-116, src/disph/d_fluid_force.cpp:26-86,
+//                    src/gsph/g_fluid_force.cpp:28-199
+//   GravityForce     src/gravity_force.cpp:52-89 -> src/bhtree.cpp:128-132,301-331
+//   TimeStep         src/timestep.cpp:18-38
+//   predict/correct  src/solver.cpp:431-474
+// One warp owns 32 consecutive particles of the sorted order; lane = particle i.  Every sum over
+// neighbours j is a warp_walk (sphb_tree.cuh) whose leaf handler streams the leaf's particles with
+// warp-uniform loads, so there are no per-particle neighbour lists in memory at all; the only
+// per-lane list is the r (and m) column of the Newton iteration, which must see one fixed
+// candidate set several times (src/pre_interaction.cpp:227-283).
+#pragma once
+#include "sphb_tree.cuh"
+
+namespace sphb {
+
+struct Counters {   // device mirror of sphb_counters (include/sphb.h), all summed over particles
+    unsigned long long newton_evals, newton_iters, pre_candidates, pre_neighbors, force_pairs,
+                       grav_pp, grav_pc, grav_node_visits, nonconverged, list_overflow;
+};
+
+template <int DIM> __device__ __forceinline__ void load_vec(double * const (&a)[3], int i, double (&o)[DIM])
+{
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) o[d] = a[d][i];
+}
+template <int DIM> __device__ __forceinline__ double dot(const double (&a)[DIM], const double (&b)[DIM])
+{
+    double s = a[0] * b[0];
+#pragma unroll
+    for (int d = 1; d < DIM; ++d) s += a[d] * b[d];
+    return s;
+}
+
+// Smoothing-length guess, src/pre_interaction.cpp:61-64.
+template <int DIM> __device__ __forceinline__ double h_guess(int ngb, double mass, double dens)
+{
+    const double x = ngb * mass / (dens * unit_ball<DIM>());
+    if (DIM == 1) return x;
+    if (DIM == 2) return sqrt(x);
+    return cbrt(x);
+}
+
+// =================================================================================================
+// initial_smoothing, src/pre_interaction.cpp:171-215: dens_i = sum_{r < h} m_j W(r, h), h = guess
+// =================================================================================================
+template <int DIM, int KT>
+struct InitSmoothV {
+    const DevParams & P; const TreeDev & t; const PSoA & p;
+    double ri[DIM], h, h2, dens;
+    KernelCoef<DIM, KT> kc;
+    __device__ __forceinline__ bool open(int idx) { return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, h); }
+    __device__ __forceinline__ void leaf(int, int first, int count)
+    {
+        for (int j = first; j < first + count; ++j) {
+            double rj[DIM], d[DIM];
+            load_vec<DIM>(p.pos, j, rj);
+            calc_r_ij<DIM>(P, ri, rj, d);
+            const double r2 = abs2_exact<DIM>(d);
+            if (r2 < h2) {
+                const double r = sqrt(r2);
+                if (r < h) dens += p.mass[j] * kc.w(r);
+            }
+        }
+    }
+};
+
+template <int DIM, int KT>
+__global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, TreeDev t, DevParams P, int n)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+    const bool valid = i < n;
+    InitSmoothV<DIM, KT> v{P, t, p};
+    v.dens = 0.0;
+    v.h = 1.0;
+    if (valid) {
+        load_vec<DIM>(p.pos, i, v.ri);
+        v.h = h_guess<DIM>(P.ngb, p.mass[i], p.dens[i]);
+    } else {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) v.ri[d] = 0.0;
+    }
+    v.h2 = __dmul_rn(v.h, v.h);
+    v.kc.init(v.h);
+    warp_walk(t, v, valid);
+    if (valid) { p.sml[i] = v.h; p.dens[i] = v.dens; }
+}
+
+// =================================================================================================
+// PreInteraction::calculation
+// =================================================================================================
+// walk 1: candidate set {j : r2 < h_search^2} (src/bhtree.cpp:251-261) -> per-lane r (and m) column
+template <int DIM, bool NEED_M>
+struct CollectV {
+    const DevParams & P; const TreeDev & t; const PSoA & p;
+    double ri[DIM], hs, hs2;
+    double * lr; double * lm;
+    int cap, cnt, lane;
+    __device__ __forceinline__ bool open(int idx) { return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, hs); }
+    __device__ __forceinline__ void leaf(int, int first, int count)
+    {
+        for (int j = first; j < first + count; ++j) {
+            double rj[DIM], d[DIM];
+            load_vec<DIM>(p.pos, j, rj);
+            calc_r_ij<DIM>(P, ri, rj, d);
+            const double r2 = abs2_exact<DIM>(d);
+            if (r2 < hs2) {
+                if (cnt < cap) {
+                    lr[cnt * 32 + lane] = sqrt(r2);
+                    if (NEED_M) lm[cnt * 32 + lane] = p.mass[j];
+                }
+                ++cnt;
+            }
+        }
+    }
+};
+
+// walk 2: sums over {j : r2 < h_search^2 and r < h_i}: density pass + Balsara / MUSCL-gradient pass
+// (the reference runs them as two loops over the same sorted list prefix,
+//  src/pre_interaction.cpp:83-103 and 116-161; the second only needs dens_i at the very end)
+template <int DIM, int KT, int SPH>
+struct DensityV {
+    const DevParams & P; const TreeDev & t; const PSoA & p;
+    int i;
+    double ri[DIM], vi[DIM], hs2, h, reach, ci, ui;
+    KernelCoef<DIM, KT> kc;
+    bool need_div;
+    // accumulators
+    double dens, dh_dens, n_i, dh_n, pres, dh_pres, v_sig_max;
+    int n_neighbor;
+    double div_v, rot_v[3];
+    double dd[DIM], du[DIM], dv[DIM][DIM];   // GSPH
+
+    __device__ __forceinline__ bool open(int idx) { return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, reach); }
+    __device__ __forceinline__ void leaf(int, int first, int count)
+    {
+        for (int j = first; j < first + count; ++j) {
+            double rj[DIM], d[DIM];
+            load_vec<DIM>(p.pos, j, rj);
+            calc_r_ij<DIM>(P, ri, rj, d);
+            const double r2 = abs2_exact<DIM>(d);
+            if (!(r2 < hs2)) continue;
+            const double r = sqrt(r2);
+            if (r >= h) continue;                       // the `break` of the sorted loop
+            ++n_neighbor;
+            const double mj = p.mass[j];
+            const double w = kc.w(r);
+            dens += mj * w;
+            double uj = 0.0;
+            if (SPH == T_SSPH) {
+                dh_dens += mj * kc.dhw(r);
+            } else if (SPH == T_DISPH) {
+                const double dhw = kc.dhw(r);
+                uj = p.ene[j];
+                n_i += w;
+                pres += mj * uj * w;
+                dh_pres += mj * uj * dhw;
+                dh_n += dhw;
+            }
+            double vij[DIM];
+            {
+                double vj[DIM];
+                load_vec<DIM>(p.vel, j, vj);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) vij[k] = vi[k] - vj[k];
+            }
+            if (j != i) {
+                const double v_sig = ci + p.sound[j] - 3.0 * dot<DIM>(d, vij) / r;
+                if (v_sig > v_sig_max) v_sig_max = v_sig;
+            }
+            if (SPH == T_GSPH) {
+                if (P.gsph2) {
+                    const double c = kc.dwc(r);
+                    const double uji = p.ene[j] - ui;
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) {
+                        const double dwa = d[a] * c;
+                        dd[a] += dwa * mj;
+                        du[a] += dwa * (mj * uji);
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) dv[k][a] += dwa * (mj * (-vij[k]));
+                    }
+                }
+            } else if (need_div) {
+                const double c = kc.dwc(r);
+                double dw[DIM];
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) dw[a] = d[a] * c;
+                const double wgt = (SPH == T_DISPH) ? mj * uj : mj;
+                div_v -= wgt * dot<DIM>(vij, dw);
+                if (DIM == 2) {
+                    rot_v[0] += (vij[0] * dw[DIM > 1 ? 1 : 0] - vij[DIM > 1 ? 1 : 0] * dw[0]) * wgt;
+                } else if (DIM == 3) {
+                    constexpr int Y = DIM > 1 ? 1 : 0, Z = DIM > 2 ? 2 : 0;
+                    rot_v[0] += (vij[Y] * dw[Z] - vij[Z] * dw[Y]) * wgt;
+                    rot_v[1] += (vij[Z] * dw[0] - vij[0] * dw[Z]) * wgt;
+                    rot_v[2] += (vij[0] * dw[Y] - vij[Y] * dw[0]) * wgt;
+                }
+            }
+        }
+    }
+};
+
+template <int DIM, int KT, int SPH>
+__global__ void __launch_bounds__(128)
+k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __restrict__ group_counter,
+                  double * __restrict__ scratch_r, double * __restrict__ scratch_m,
+                  const double * __restrict__ d_dt, double * __restrict__ d_hpvs,
+                  unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt)
+{
+    constexpr bool NEED_M = (SPH != T_DISPH);     // DISPH Newton uses unit weights (d_pre_interaction.cpp:208-209)
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    double * lr = scratch_r + (size_t)slot * P.list_cap * 32;
+    double * lm = NEED_M ? scratch_m + (size_t)slot * P.list_cap * 32 : nullptr;
+    const double dt = *d_dt;
+    double hpvs_min = 1.7976931348623157e308;
+    unsigned long long c_evals = 0, c_iters = 0, c_cand = 0, c_ngb = 0, c_nonconv = 0, c_over = 0;
+
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(group_counter, 1);
+        g = __shfl_sync(SPHB_FULL_MASK, g, 0);
+        if (g >= g_end) break;
+        const int i = g * 32 + lane;
+        const bool valid = i < n;
+
+        double ri[DIM], vi[DIM];
+        double mass_i = 1.0, dens_old = 1.0, ene_i = 0.0, c_i = 0.0, alpha_i = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { ri[d] = 0.0; vi[d] = 0.0; }
+        if (valid) {
+            load_vec<DIM>(p.pos, i, ri);
+            load_vec<DIM>(p.vel, i, vi);
+            mass_i = p.mass[i]; dens_old = p.dens[i]; ene_i = p.ene[i]; c_i = p.sound[i]; alpha_i = p.alpha[i];
+        }
+        // guess smoothing length (src/pre_interaction.cpp:61-64)
+        const double hs = h_guess<DIM>(P.ngb, mass_i, dens_old) * P.kernel_ratio;
+        const double hs2 = __dmul_rn(hs, hs);
+        double h = hs;
+
+        if (P.iterative) {
+            // ---- walk 1: candidates
+            CollectV<DIM, NEED_M> cv{P, t, p};
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) cv.ri[d] = ri[d];
+            cv.hs = hs; cv.hs2 = hs2; cv.lr = lr; cv.lm = lm; cv.cap = P.list_cap; cv.cnt = 0; cv.lane = lane;
+            warp_walk(t, cv, valid);
+            int ncand = cv.cnt;
+            if (ncand > P.list_cap) { ++c_over; ncand = P.list_cap; }
+            c_cand += valid ? ncand : 0;
+            __syncwarp();
+            // ---- Newton-Raphson (src/pre_interaction.cpp:227-283)
+            const double h0 = hs / P.kernel_ratio;
+            const double b = NEED_M ? mass_i * P.ngb / unit_ball<DIM>() : P.ngb / unit_ball<DIM>();
+            h = h0;
+            bool done = !valid, conv = false;
+            for (int it = 0; it < 10; ++it) {
+                if (!__any_sync(SPHB_FULL_MASK, !done)) break;
+                if (!done) {
+                    KernelCoef<DIM, KT> kc;
+                    kc.init(h);
+                    double s = 0.0, sd = 0.0;
+                    for (int k = 0; k < ncand; ++k) {
+                        const double r = lr[k * 32 + lane];
+                        if (r < h) {
+                            if (NEED_M) {
+                                const double m = lm[k * 32 + lane];
+                                s += m * kc.w(r);
+                                sd += m * kc.dhw(r);
+                            } else {
+                                s += kc.w(r);
+                                sd += kc.dhw(r);
+                            }
+                            ++c_evals;
+                        }
+                    }
+                    ++c_iters;
+                    const double f = s * powh<DIM>(h) - b;
+                    const double df = sd * powh<DIM>(h) + DIM * s * powh_<DIM>(h);
+                    const double hn = h - f / df;
+                    if (fabs(hn - h) < (hn + h) * 1e-4) { done = true; conv = true; }
+                    h = hn;
+                }
+            }
+            if (valid && !conv) { h = h0; ++c_nonconv; }    // logged + fallback, pre_interaction.cpp:277-282
+            __syncwarp();
+        }
+
+        // ---- walk 2: density pass (+ Balsara / MUSCL gradients)
+        DensityV<DIM, KT, SPH> dv{P, t, p};
+        dv.i = i;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) { dv.ri[d] = ri[d]; dv.vi[d] = vi[d]; }
+        dv.hs2 = hs2; dv.h = h; dv.reach = fmin(h, hs); dv.ci = c_i; dv.ui = ene_i;
+        dv.kc.init(h);
+        dv.need_div = (SPH != T_GSPH) && ((P.use_balsara && DIM != 1) || P.use_tdav);
+        dv.dens = dv.dh_dens = dv.n_i = dv.dh_n = dv.pres = dv.dh_pres = 0.0;
+        dv.v_sig_max = c_i * 2.0;
+        dv.n_neighbor = 0;
+        dv.div_v = 0.0; dv.rot_v[0] = dv.rot_v[1] = dv.rot_v[2] = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            dv.dd[a] = 0.0; dv.du[a] = 0.0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) dv.dv[k][a] = 0.0;
+        }
+        warp_walk(t, dv, valid);
+
+        if (valid) {
+            const double dens_i = dv.dens;
+            double pres_i, div_norm;
+            if (SPH == T_SSPH) {
+                pres_i = (P.gamma - 1.0) * dens_i * ene_i;
+                p.gradh[i] = 1.0 / (1.0 + h / (DIM * dens_i) * dv.dh_dens);
+                div_norm = 1.0 / dens_i;
+            } else if (SPH == T_DISPH) {
+                pres_i = (P.gamma - 1.0) * dv.pres;
+                p.gradh[i] = h / (DIM * dv.n_i) * dv.dh_pres / (1.0 + h / (DIM * dv.n_i) * dv.dh_n);
+                div_norm = (P.gamma - 1.0) / pres_i;
+            } else {
+                pres_i = (P.gamma - 1.0) * dens_i * ene_i;
+                div_norm = 0.0;
+            }
+            p.sml[i] = h;
+            p.dens[i] = dens_i;
+            p.pres[i] = pres_i;
+            p.neighbor[i] = dv.n_neighbor;
+            c_ngb += dv.n_neighbor;
+            hpvs_min = fmin(hpvs_min, h / dv.v_sig_max);
+
+            if (SPH == T_GSPH) {
+                if (P.gsph2) {
+                    const double rho_inv = 1.0 / dens_i;
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) {
+                        p.grad_d[a][i] = dv.dd[a];
+                        p.grad_p[a][i] = (dv.dd[a] * ene_i + dv.du[a]) * (P.gamma - 1.0);
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) p.grad_v[k][a][i] = dv.dv[k][a] * rho_inv;
+                    }
+                }
+            } else if (P.use_balsara && DIM != 1) {
+                const double div_v = (SPH == T_SSPH) ? dv.div_v / dens_i : dv.div_v * div_norm;
+                double rot_abs;
+                if (DIM == 2) {
+                    rot_abs = fabs((SPH == T_SSPH) ? dv.rot_v[0] / dens_i : dv.rot_v[0] * div_norm);
+                } else {
+                    double rr[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) rr[a] = (SPH == T_SSPH) ? dv.rot_v[a] / dens_i : dv.rot_v[a] * div_norm;
+                    rot_abs = sqrt(rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2]);
+                }
+                p.balsara[i] = fabs(div_v) / (fabs(div_v) + rot_abs + 1e-4 * c_i / h);
+                if (P.use_tdav) {
+                    const double tau_inv = P.epsilon_av * c_i / h;
+                    const double dalpha = (-(alpha_i - P.alpha_min) * tau_inv + fmax(-div_v, 0.0) * (P.alpha_max - alpha_i)) * dt;
+                    p.alpha[i] = alpha_i + dalpha;
+                }
+            } else if (P.use_tdav) {
+                const double div_v = (SPH == T_SSPH) ? dv.div_v / dens_i : dv.div_v * div_norm;
+                const double tau_inv = P.epsilon_av * c_i / h;
+                const double s_i = fmax(-div_v, 0.0);
+                p.alpha[i] = (alpha_i + dt * tau_inv * P.alpha_min + s_i * dt * P.alpha_max) / (1.0 + dt * tau_inv + s_i * dt);
+            }
+        }
+    }
+
+    hpvs_min = warp_min(hpvs_min);
+    if (lane == 0) atomic_min_pos(d_hpvs, hpvs_min);
+    if (cnt) {
+        c_evals = warp_sum_u64(c_evals); c_iters = warp_sum_u64(c_iters); c_cand = warp_sum_u64(c_cand);
+        c_ngb = warp_sum_u64(c_ngb);
+    }
+    c_nonconv = warp_sum_u64(c_nonconv); c_over = warp_sum_u64(c_over);
+    if (lane == 0) {
+        if (cnt) {
+            atomicAdd(&cnt->newton_evals, c_evals); atomicAdd(&cnt->newton_iters, c_iters);
+            atomicAdd(&cnt->pre_candidates, c_cand); atomicAdd(&cnt->pre_neighbors, c_ngb);
+        }
+    }
+    if (lane == 0 && (c_nonconv | c_over)) {      // always-on error counters
+        atomicAdd(&d_err[0], c_nonconv);
+        atomicAdd(&d_err[1], c_over);
+    }
+}
+
+// =================================================================================================
+// FluidForce::calculation — symmetric pair set {j : r2 < max(h_i, ksize(leaf))^2, 0 < r < max(h_i, h_j)}
+// =================================================================================================
+// Monaghan (1997) signal-velocity viscosity, src/fluid_force.cpp:89-106
+__device__ __forceinline__ double art_visc(double vr, double r, double ci, double cj, double ai, double aj,
+                                           double bi, double bj, double di, double dj)
+{
+    if (vr < 0) {
+        const double alpha = 0.5 * (ai + aj);
+        const double balsara = 0.5 * (bi + bj);
+        const double w_ij = vr / r;
+        const double v_sig = ci + cj - 3.0 * w_ij;
+        const double rho_ij_inv = 2.0 / (di + dj);
+        return -0.5 * balsara * alpha * v_sig * w_ij * rho_ij_inv;
+    }
+    return 0.0;
+}
+
+// van Leer (1979) limiter, src/gsph/g_fluid_force.cpp:28-36
+__device__ __forceinline__ double van_leer(double dq1, double dq2)
+{
+    const double dq1dq2 = dq1 * dq2;
+    if (dq1dq2 <= 0) return 0.0;
+    return 2.0 * dq1dq2 / (dq1 + dq2);
+}
+
+// HLL solver, src/gsph/g_fluid_force.cpp:168-199.  state = {u, rho, p, c}
+__device__ __forceinline__ void hll(const double (&left)[4], const double (&right)[4], double & pstar, double & vstar)
+{
+    const double u_l = left[0], rho_l = left[1], p_l = left[2], c_l = left[3];
+    const double u_r = right[0], rho_r = right[1], p_r = right[2], c_r = right[3];
+    const double roe_l = sqrt(rho_l);
+    const double roe_r = sqrt(rho_r);
+    const double roe_inv = 1.0 / (roe_l + roe_r);
+    const double u_t = (roe_l * u_l + roe_r * u_r) * roe_inv;
+    const double c_t = (roe_l * c_l + roe_r * c_r) * roe_inv;
+    const double s_l = fmin(u_l - c_l, u_t - c_t);
+    const double s_r = fmax(u_r + c_r, u_t + c_t);
+    const double c1 = rho_l * (s_l - u_l);
+    const double c2 = rho_r * (s_r - u_r);
+    const double c3 = 1.0 / (c1 - c2);
+    const double c4 = p_l - u_l * c1;
+    const double c5 = p_r - u_r * c2;
+    vstar = (c5 - c4) * c3;
+    pstar = (c1 * c5 - c2 * c4) * c3;
+}
+
+template <int DIM, int KT, int SPH>
+struct ForceV {
+    const DevParams & P; const TreeDev & t; const PSoA & p;
+    int i;
+    double dt;
+    double ri[DIM], vi[DIM], h_i, m_i, dens_i, pres_i, gradh_i, alpha_i, bal_i, c_i, u_i;
+    double gdi[DIM], gpi[DIM], gvi[DIM][DIM];          // GSPH gradients of i
+    double pp_i;            // SSPH: P_i/rho_i^2 * gradh_i ; DISPH: (g-1)^2 u_i / P_i ; GSPH: 1/rho_i^2
+    double g2u_i;           // DISPH: (g-1)^2 u_i
+    double m_u_inv;         // DISPH: 1/(m_i u_i)
+    KernelCoef<DIM, KT> ki;
+    double acc[DIM], dene;
+    unsigned long long pairs;
+
+    __device__ __forceinline__ bool open(int idx)
+    {
+        const double h = fmax(h_i, __ldg(&t.ksize[idx]));           // src/bhtree.cpp:237
+        return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, h);
+    }
+    __device__ __forceinline__ void leaf(int idx, int first, int count)
+    {
+        const double h = fmax(h_i, __ldg(&t.ksize[idx]));
+        const double h2 = __dmul_rn(h, h);
+        for (int j = first; j < first + count; ++j) {
+            double rj[DIM], d[DIM];
+            load_vec<DIM>(p.pos, j, rj);
+            calc_r_ij<DIM>(P, ri, rj, d);
+            const double r2 = abs2_exact<DIM>(d);
+            if (!(r2 < h2)) continue;                               // src/bhtree.cpp:255-256
+            const double h_j = p.sml[j];
+            const double r = sqrt(r2);
+            if (r >= fmax(h_i, h_j) || r == 0.0) continue;          // src/fluid_force.cpp:62
+            ++pairs;
+            KernelCoef<DIM, KT> kj;
+            kj.init(h_j);
+            const double cwi = ki.dwc(r), cwj = kj.dwc(r);
+            double dw_i[DIM], dw_j[DIM], vij[DIM], vj[DIM];
+            load_vec<DIM>(p.vel, j, vj);
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) { dw_i[a] = d[a] * cwi; dw_j[a] = d[a] * cwj; vij[a] = vi[a] - vj[a]; }
+            const double m_j = p.mass[j];
+            const double dens_j = p.dens[j], pres_j = p.pres[j];
+
+            if (SPH == T_GSPH) {
+                const double c_j = p.sound[j];
+                const double r_inv = 1.0 / r;
+                double e[DIM];
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) e[a] = d[a] * r_inv;
+                const double ve_i = dot<DIM>(vi, e);
+                const double ve_j = dot<DIM>(vj, e);
+                double vstar, pstar;
+                if (P.gsph2) {
+                    // Murante et al. (2011), src/gsph/g_fluid_force.cpp:96-134
+                    double right[4], left[4];
+                    const double delta_i = 0.5 * (1.0 - c_i * dt * r_inv);
+                    const double delta_j = 0.5 * (1.0 - c_j * dt * r_inv);
+                    const double dv_ij = ve_i - ve_j;
+                    double dvi[DIM], dvj[DIM], gdj[DIM], gpj[DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) {
+                        double gvj[DIM];
+#pragma unroll
+                        for (int a = 0; a < DIM; ++a) gvj[a] = p.grad_v[k][a][j];
+                        dvi[k] = dot<DIM>(gvi[k], e);
+                        dvj[k] = dot<DIM>(gvj, e);
+                    }
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) { gdj[a] = p.grad_d[a][j]; gpj[a] = p.grad_p[a][j]; }
+                    const double dve_i = dot<DIM>(dvi, e) * r;
+                    const double dve_j = dot<DIM>(dvj, e) * r;
+                    right[0] = ve_i - van_leer(dv_ij, dve_i) * delta_i;
+                    left[0] = ve_j + van_leer(dv_ij, dve_j) * delta_j;
+                    const double dd_ij = dens_i - dens_j;
+                    const double dd_i = dot<DIM>(gdi, e) * r;
+                    const double dd_j = dot<DIM>(gdj, e) * r;
+                    right[1] = dens_i - van_leer(dd_ij, dd_i) * delta_i;
+                    left[1] = dens_j + van_leer(dd_ij, dd_j) * delta_j;
+                    const double dp_ij = pres_i - pres_j;
+                    const double dp_i = dot<DIM>(gpi, e) * r;
+                    const double dp_j = dot<DIM>(gpj, e) * r;
+                    right[2] = pres_i - van_leer(dp_ij, dp_i) * delta_i;
+                    left[2] = pres_j + van_leer(dp_ij, dp_j) * delta_j;
+                    right[3] = sqrt(P.gamma * right[2] / right[1]);
+                    left[3] = sqrt(P.gamma * left[2] / left[1]);
+                    hll(left, right, pstar, vstar);
+                } else {
+                    const double right[4] = {ve_i, dens_i, pres_i, c_i};
+                    const double left[4] = {ve_j, dens_j, pres_j, c_j};
+                    hll(left, right, pstar, vstar);
+                }
+                const double rho2_inv_j = 1.0 / (dens_j * dens_j);
+                double fdotv = 0.0;
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) {
+                    const double f = dw_i[a] * (m_j * pstar * pp_i) + dw_j[a] * (m_j * pstar * rho2_inv_j);
+                    acc[a] -= f;
+                    fdotv += f * (e[a] * vstar - vi[a]);
+                }
+                dene -= fdotv;
+            } else {
+                const double c_j = p.sound[j];
+                const double vr = dot<DIM>(vij, d);
+                const double pi_ij = art_visc(vr, r, c_i, c_j, alpha_i, p.alpha[j], bal_i, p.balsara[j], dens_i, dens_j);
+                double dw_ij[DIM];
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) dw_ij[a] = (dw_i[a] + dw_j[a]) * 0.5;
+                const double u_j = p.ene[j];
+                double dene_ac = 0.0;
+                if (P.use_ac) {
+                    // src/fluid_force.cpp:108-116
+                    const double v_sig = P.use_gravity ? fabs(vr / r) : sqrt(2.0 * fabs(pres_i - pres_j) / (dens_i + dens_j));
+                    dene_ac = P.alpha_ac * m_j * v_sig * (u_i - u_j) * dot<DIM>(dw_ij, d) / r;
+                }
+                double ti, tj, ei;
+                if (SPH == T_SSPH) {
+                    // src/fluid_force.cpp:78-79
+                    ti = m_j * (pp_i + 0.5 * pi_ij);
+                    tj = m_j * (pres_j / (dens_j * dens_j) * p.gradh[j] + 0.5 * pi_ij);
+                    ei = m_j * pp_i;
+                } else {
+                    // src/disph/d_fluid_force.cpp:70-79
+                    const double f_ij = 1.0 - gradh_i / (m_j * u_j);
+                    const double f_ji = 1.0 - p.gradh[j] * m_u_inv;
+                    const double u_per_pres_j = u_j / pres_j;
+                    ti = m_j * (pp_i * u_j * f_ij + 0.5 * pi_ij);
+                    tj = m_j * (g2u_i * u_per_pres_j * f_ji + 0.5 * pi_ij);
+                    ei = m_j * pp_i * u_j * f_ij;
+                }
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) acc[a] -= dw_i[a] * ti + dw_j[a] * tj;
+                dene += ei * dot<DIM>(vij, dw_i) + 0.5 * m_j * pi_ij * dot<DIM>(vij, dw_ij) + dene_ac;
+            }
+        }
+    }
+};
+
+template <int DIM, int KT, int SPH>
+__global__ void __launch_bounds__(128)
+k_fluid_force(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const double * __restrict__ d_dt,
+              Counters * __restrict__ cnt)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = i_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+    const bool valid = i < i_end;
+    ForceV<DIM, KT, SPH> v{P, t, p};
+    v.i = i;
+    v.dt = *d_dt;
+    v.pairs = 0;
+    v.dene = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { v.acc[a] = 0.0; v.ri[a] = 0.0; v.vi[a] = 0.0; }
+    v.h_i = 1.0; v.m_i = 1.0; v.dens_i = 1.0; v.pres_i = 1.0; v.gradh_i = 0.0; v.alpha_i = 0.0; v.bal_i = 0.0; v.c_i = 0.0; v.u_i = 1.0;
+    if (valid) {
+        load_vec<DIM>(p.pos, i, v.ri);
+        load_vec<DIM>(p.vel, i, v.vi);
+        v.h_i = p.sml[i]; v.m_i = p.mass[i]; v.dens_i = p.dens[i]; v.pres_i = p.pres[i];
+        v.c_i = p.sound[i]; v.u_i = p.ene[i];
+        if (SPH != T_GSPH) { v.gradh_i = p.gradh[i]; v.alpha_i = p.alpha[i]; v.bal_i = p.balsara[i]; }
+        if (SPH == T_GSPH && P.gsph2) {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+                v.gdi[a] = p.grad_d[a][i]; v.gpi[a] = p.grad_p[a][i];
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) v.gvi[k][a] = p.grad_v[k][a][i];
+            }
+        }
+    }
+    if (SPH == T_SSPH) {
+        v.pp_i = v.pres_i / (v.dens_i * v.dens_i) * v.gradh_i;
+    } else if (SPH == T_DISPH) {
+        v.g2u_i = (P.gamma - 1.0) * (P.gamma - 1.0) * v.u_i;
+        v.pp_i = v.g2u_i / v.pres_i;
+        v.m_u_inv = 1.0 / (v.m_i * v.u_i);
+    } else {
+        v.pp_i = 1.0 / (v.dens_i * v.dens_i);
+    }
+    v.ki.init(v.h_i);
+    warp_walk(t, v, valid);
+    if (valid) {
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) p.acc[a][i] = v.acc[a];
+        p.dene[i] = v.dene;
+    }
+    if (cnt) {
+        const unsigned long long s = warp_sum_u64(valid ? v.pairs : 0ull);
+        if (lane == 0) atomicAdd(&cnt->force_pairs, s);
+    }
+}
+
+// =================================================================================================
+// GravityForce::calculation -> BHNode::calc_force, src/bhtree.cpp:301-331
+// =================================================================================================
+template <int DIM>
+struct GravityV {
+    const DevParams & P; const TreeDev & t; const PSoA & p;
+    double ri[DIM], h_i, einv_i, acc[DIM], phi;
+    unsigned long long n_pp, n_pc, n_visit;
+
+    __device__ __forceinline__ bool open(int idx)
+    {
+        ++n_visit;
+        const double4 c = ldg4(&t.com[idx]);
+        const double edge = ldg4(&t.geo[idx]).w;
+        double cm[DIM], d[DIM];
+        cm[0] = c.x;
+        if (DIM >= 2) cm[DIM >= 2 ? 1 : 0] = c.y;
+        if (DIM >= 3) cm[DIM >= 3 ? 2 : 0] = c.z;
+        calc_r_ij<DIM>(P, ri, cm, d);
+        const double d2 = abs2_exact<DIM>(d);
+        const double l2 = __dmul_rn(edge, edge);
+        if (l2 > __dmul_rn(P.theta2, d2)) return true;
+        // monopole, src/bhtree.cpp:326-330
+        const double r_inv = 1.0 / sqrt(d2);
+        const double gm = P.G * c.w;
+        phi -= gm * r_inv;
+        const double s = gm * (r_inv * r_inv * r_inv);
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
+        ++n_pc;
+        return false;
+    }
+    __device__ __forceinline__ void leaf(int, int first, int count)
+    {
+        for (int j = first; j < first + count; ++j) {
+            double rj[DIM], d[DIM];
+            load_vec<DIM>(p.pos, j, rj);
+            calc_r_ij<DIM>(P, ri, rj, d);
+            const double r2 = abs2_exact<DIM>(d);
+            const double r = sqrt(r2);
+            const double rinv = 1.0 / r;               // inf at r == 0, unused there (u < 1 branch)
+            const double einv_j = 2.0 / p.sml[j];
+            double fi, gi, fj, gj;
+            soft_fg(r, rinv, einv_i, fi, gi);
+            soft_fg(r, rinv, einv_j, fj, gj);
+            const double gm = P.G * p.mass[j];
+            phi -= gm * (fi + fj) * 0.5;
+            const double s = gm * (gi + gj) * 0.5;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
+            ++n_pp;
+        }
+    }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(128)
+k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, Counters * __restrict__ cnt)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = i_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+    const bool valid = i < i_end;
+    GravityV<DIM> v{P, t, p};
+    v.n_pp = v.n_pc = v.n_visit = 0;
+    v.phi = 0.0;                                    // src/bhtree.cpp:130
+    v.h_i = 1.0;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { v.ri[a] = 0.0; v.acc[a] = 0.0; }
+    if (valid) {
+        load_vec<DIM>(p.pos, i, v.ri);
+        load_vec<DIM>(p.acc, i, v.acc);             // gravity adds onto the fluid acceleration
+        v.h_i = p.sml[i];
+    }
+    v.einv_i = 2.0 / v.h_i;
+    warp_walk(t, v, valid);
+    if (valid) {
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) p.acc[a][i] = v.acc[a];
+        p.phi[i] = v.phi;
+    }
+    if (cnt) {
+        const unsigned long long a = warp_sum_u64(valid ? v.n_pp : 0ull), b = warp_sum_u64(valid ? v.n_pc : 0ull),
+                                 c = warp_sum_u64(valid ? v.n_visit : 0ull);
+        if (lane == 0) { atomicAdd(&cnt->grav_pp, a); atomicAdd(&cnt->grav_pc, b); atomicAdd(&cnt->grav_node_visits, c); }
+    }
+}
+
+// Direct sum, the EXHAUSTIVE_SEARCH flavour of GravityForce (src/gravity_force.cpp:70-84).
+template <int DIM>
+__global__ void __launch_bounds__(128) k_gravity_direct(PSoA p, DevParams P, int n)
+{
+    __shared__ double sx[DIM][128], sm[128], sh[128];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    double ri[DIM], f[DIM], phi = 0.0, h_i = 1.0;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) { ri[a] = 0.0; f[a] = 0.0; }
+    if (valid) { load_vec<DIM>(p.pos, i, ri); h_i = p.sml[i]; }
+    const double einv_i = 2.0 / h_i;
+    for (int base = 0; base < n; base += 128) {
+        const int j = base + threadIdx.x;
+        __syncthreads();
+        if (j < n) {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) sx[a][threadIdx.x] = p.pos[a][j];
+            sm[threadIdx.x] = p.mass[j];
+            sh[threadIdx.x] = p.sml[j];
+        }
+        __syncthreads();
+        const int m = min(128, n - base);
+        for (int k = 0; k < m; ++k) {
+            double rj[DIM], d[DIM];
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) rj[a] = sx[a][k];
+            calc_r_ij<DIM>(P, ri, rj, d);
+            const double r = sqrt(abs2_exact<DIM>(d));
+            const double rinv = 1.0 / r;
+            double fi, gi, fj, gj;
+            soft_fg(r, rinv, einv_i, fi, gi);
+            soft_fg(r, rinv, 2.0 / sh[k], fj, gj);
+            const double gm = P.G * sm[k];
+            phi -= gm * (fi + fj) * 0.5;
+            const double s = gm * (gi + gj) * 0.5;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) f[a] -= d[a] * s;
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) p.acc[a][i] += f[a];
+        p.phi[i] = phi;
+    }
+}
+
+// =================================================================================================
+// TimeStep::calculation (src/timestep.cpp:18-38): dt[0] = min(cflSound * h_per_v_sig, cflForce * min sqrt(h/|a|))
+// =================================================================================================
+template <int DIM>
+__global__ void k_timestep_partial(PSoA p, int i_begin, int i_end, double c_force, double * __restrict__ d_min)
+{
+    double m = 1.7976931348623157e308;
+    for (int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x; i < i_end; i += gridDim.x * blockDim.x) {
+        double a[DIM];
+        load_vec<DIM>(p.acc, i, a);
+        const double acc_abs = sqrt(dot<DIM>(a, a));
+        if (acc_abs > 0.0) {
+            const double dt_force_i = c_force * sqrt(p.sml[i] / acc_abs);
+            if (dt_force_i < m) m = dt_force_i;
+        }
+    }
+    m = warp_min(m);
+    if ((threadIdx.x & 31) == 0) atomic_min_pos(d_min, m);
+}
+__global__ void k_timestep_final(const double * __restrict__ d_min, const double * __restrict__ d_hpvs, double c_sound, double * __restrict__ d_dt)
+{
+    const double dt_sound = c_sound * d_hpvs[0];
+    d_dt[0] = fmin(dt_sound, d_min[0]);
+}
+
+// =================================================================================================
+// Solver::predict / correct (src/solver.cpp:431-474) and the post-IC state (392-404)
+// =================================================================================================
+template <int DIM>
+__global__ void k_predict(PSoA p, DevParams P, int n, const double * __restrict__ d_dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dt = *d_dt;
+    const double c_sound = P.gamma * (P.gamma - 1.0);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        const double v = p.vel[d][i], a = p.acc[d][i];
+        const double vp = v + a * (0.5 * dt);
+        p.vel_p[d][i] = vp;
+        double x = p.pos[d][i] + vp * dt;
+        p.vel[d][i] = v + a * dt;
+        if (P.periodic) {                              // Periodic::apply, include/periodic.hpp:61-72
+            if (x < P.rmin[d]) x += P.range[d];
+            else if (x > P.rmax[d]) x -= P.range[d];
+        }
+        p.pos[d][i] = x;
+    }
+    const double u = p.ene[i], du = p.dene[i];
+    p.ene_p[i] = u + du * (0.5 * dt);
+    const double un = u + du * dt;
+    p.ene[i] = un;
+    p.sound[i] = sqrt(c_sound * un);
+}
+
+template <int DIM>
+__global__ void k_correct(PSoA p, DevParams P, int n, const double * __restrict__ d_dt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dt = *d_dt;
+    const double c_sound = P.gamma * (P.gamma - 1.0);
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) p.vel[d][i] = p.vel_p[d][i] + p.acc[d][i] * (0.5 * dt);
+    const double un = p.ene_p[i] + p.dene[i] * (0.5 * dt);
+    p.ene[i] = un;
+    p.sound[i] = sqrt(c_sound * un);
+}
+
+__global__ void k_init_state(PSoA p, DevParams P, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    p.alpha[i] = P.av_alpha;
+    p.balsara[i] = 1.0;
+    p.sound[i] = sqrt(P.gamma * (P.gamma - 1.0) * p.ene[i]);
+}
+
+// Output::output_energy sums, src/output.cpp:72-83: out = {kinetic, thermal, potential}
+template <int DIM>
+__global__ void k_energy(PSoA p, int n, double * __restrict__ out)
+{
+    double ek = 0.0, et = 0.0, ep = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double v[DIM];
+        load_vec<DIM>(p.vel, i, v);
+        const double m = p.mass[i];
+        ek += 0.5 * m * dot<DIM>(v, v);
+        et += m * p.ene[i];
+        ep += 0.5 * m * p.phi[i];
+    }
+    ek = warp_sum(ek); et = warp_sum(et); ep = warp_sum(ep);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], ek); atomicAdd(&out[1], et); atomicAdd(&out[2], ep); }
+}
+
+// =================================================================================================
+// test hook: explicit neighbour lists (sphb_neighbor_lists)
+// =================================================================================================
+template <int DIM>
+struct ListV {
+    const DevParams & P; const TreeDev & t; const PSoA & p;
+    double ri[DIM], h_i, h_i2;
+    bool symmetric, fill;
+    int cnt;
+    int * out;           // fill: write p.orig[j] at out[cnt]
+    long long cap_left;
+    __device__ __forceinline__ bool open(int idx)
+    {
+        const double h = symmetric ? fmax(h_i, __ldg(&t.ksize[idx])) : h_i;
+        return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, h);
+    }
+    __device__ __forceinline__ void leaf(int, int first, int count)
+    {
+        for (int j = first; j < first + count; ++j) {
+            double rj[DIM], d[DIM];
+            load_vec<DIM>(p.pos, j, rj);
+            calc_r_ij<DIM>(P, ri, rj, d);
+            const double r2 = abs2_exact<DIM>(d);
+            double k2 = h_i2;
+            if (symmetric) { const double hj = p.sml[j]; k2 = fmax(h_i2, __dmul_rn(hj, hj)); }   // exhaustive_search.cpp:28
+            if (r2 < k2) {
+                if (fill && cnt < cap_left) out[cnt] = p.orig[j];
+                ++cnt;
+            }
+        }
+    }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(128)
+k_neighbor_lists(PSoA p, TreeDev t, DevParams P, int n, const double * __restrict__ h_override /* sorted order or null */,
+                 int symmetric, int fill, int * __restrict__ counts, const long long * __restrict__ offsets,
+                 int * __restrict__ ids, long long cap_total)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+    const bool valid = i < n;
+    ListV<DIM> v{P, t, p};
+    v.symmetric = symmetric != 0; v.fill = fill != 0; v.cnt = 0; v.out = nullptr; v.cap_left = 0;
+    v.h_i = 1.0;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) v.ri[a] = 0.0;
+    if (valid) {
+        load_vec<DIM>(p.pos, i, v.ri);
+        v.h_i = h_override ? h_override[i] : p.sml[i];
+        if (fill) {
+            const long long o = offsets[i];
+            v.out = ids + (o < cap_total ? o : 0);
+            v.cap_left = o < cap_total ? cap_total - o : 0;
+        }
+    }
+    v.h_i2 = __dmul_rn(v.h_i, v.h_i);
+    warp_walk(t, v, valid);
+    if (valid && !fill) counts[i] = v.cnt;
+}
+
+// FP64 FMA micro-benchmark (roofline denominator)
+__global__ void k_fp64_peak(double * out, int iters)
+{
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int k = 0; k < iters; ++k) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+} // namespace sphb
