@@ -214,10 +214,12 @@ int alloc_particles(sphb_ctx * c, int n)
     return 0;
 }
 
-int alloc_nodes(sphb_ctx * c, int cap, int keep)
+int alloc_nodes(sphb_ctx * c, int cap, int keep, int keep_offs = 0)
 {
-    // (re)allocate node arrays with capacity `cap`, preserving the first `keep` BFS nodes
+    // (re)allocate node arrays with capacity `cap`, preserving the first `keep` BFS nodes and the
+    // first `keep_offs` child offsets of the level being emitted
     TreeBuild old = c->tb;
+    int * old_offs = c->lvl_offs;
     std::vector<void *> old_bag;
     old_bag.swap(c->node_allocs);
     TreeBuild & t = c->tb;
@@ -235,6 +237,7 @@ int alloc_nodes(sphb_ctx * c, int cap, int keep)
     }
     if (dev_alloc(c, &t.msum, cap, c->node_allocs)) return 1;
     if (dev_alloc(c, &c->lvl_tmp, cap, c->node_allocs) || dev_alloc(c, &c->lvl_offs, cap, c->node_allocs)) return 1;
+    if (keep_offs) CK(cudaMemcpyAsync(c->lvl_offs, old_offs, (size_t)keep_offs * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     TreeDev & o = c->td;
     if (dev_alloc(c, &o.meta, cap, c->node_allocs) || dev_alloc(c, &o.geo, cap, c->node_allocs) ||
         dev_alloc(c, &o.com, cap, c->node_allocs) || dev_alloc(c, &o.ksize, cap, c->node_allocs) ||
@@ -358,7 +361,7 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         if ((long long)le + total > node_limit) { c->err = "There is no free node."; return 1; }    // src/bhtree.cpp:179-181
         if (le + total > c->node_cap) {
             const int ncap = (int)std::min<long long>(node_limit, std::max<long long>(2LL * c->node_cap, (long long)le + total + 1024));
-            if (alloc_nodes(c, ncap, le)) return 1;
+            if (alloc_nodes(c, ncap, le, w)) return 1;
         }
         k_level_emit<DIM><<<cdiv(w, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_offs, c->d_root);
         LAUNCH_CHECK();

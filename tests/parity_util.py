@@ -60,9 +60,12 @@ def field_errors(got, ref):
         a_scale = np.where(h > 0, c * c / h, 0.0)
         e_scale = np.where(h > 0, c * c * c / h, 0.0)
     out = {}
-    for f in ("sml", "dens", "pres", "gradh", "balsara", "alpha", "sound", "ene", "ene_p", "phi", "mass"):
+    for f in ("sml", "dens", "pres", "gradh", "alpha", "sound", "ene", "ene_p", "phi", "mass"):
         d = np.abs(got[f] - ref[f])
         out[f] = float(np.max(d / np.maximum(np.abs(ref[f]), 1e-300)))
+    # the Balsara switch |div v| / (|div v| + |rot v| + 1e-4 c/h) lives in [0, 1]; where div v is pure
+    # cancellation noise (uniform lattice) only its absolute value is meaningful
+    out["balsara"] = float(np.max(np.abs(got["balsara"] - ref["balsara"])))
     for f, floor in (("acc", a_scale), ("vel", c), ("vel_p", c)):
         d = vnorm(got[f] - ref[f])
         out[f] = float(np.max(d / np.maximum(vnorm(ref[f]) + floor, 1e-300)))
@@ -75,8 +78,31 @@ def field_errors(got, ref):
     return out
 
 
-def assert_fields(got, ref, fields, rtol=RTOL, what=""):
+def boundary_ties(ref, params, idx, tol=1e-12):
+    """For particles idx: number of j whose minimum-image distance sits within tol (relative) of the
+    support radius h_i.  SPHParticle::neighbor counts `r < h_i`; on exact lattices (1-D shock tube:
+    h converges to 2 dx) a neighbour can sit ON the support boundary, where W = 0 and the count is
+    decided by the last bit of h, i.e. by the reference compiler's -ffast-math code generation."""
+    pos = ref["pos"]
+    out = []
+    for i in idx:
+        d = pos[i] - pos
+        if params["periodic"]:
+            L = np.asarray(params["rangeMax"]) - np.asarray(params["rangeMin"])
+            d = d - L * np.round(d / L)
+        r = np.sqrt((d * d).sum(axis=1))
+        out.append(int(np.sum(np.abs(r - ref["sml"][i]) <= tol * ref["sml"][i])))
+    return np.array(out)
+
+
+def assert_fields(got, ref, fields, rtol=RTOL, what="", params=None):
     e = field_errors(got, ref)
+    if params is not None and "neighbor" in fields and e["neighbor"]:
+        idx = np.nonzero(got["neighbor"] != ref["neighbor"])[0]
+        ties = boundary_ties(ref, params, idx)
+        if np.all(np.abs(got["neighbor"][idx].astype(int) - ref["neighbor"][idx]) <= ties):
+            e["neighbor_boundary_ties"] = e["neighbor"]
+            e["neighbor"] = 0
     bad = {f: e[f] for f in fields if (e[f] > (0 if f in ("neighbor", "id") else rtol) or not np.isfinite(e[f]))}
     assert not bad, f"{what}: fields beyond rtol={rtol}: {bad} (all: {e})"
     return e
