@@ -57,7 +57,8 @@ struct sphb_ctx {
     int dim = 0, device = 0;
     sphb_params hp{};
     DevParams P{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream all work is issued on
+    cudaStream_t own_stream = nullptr;   // created by sphb_create, destroyed by sphb_destroy
     int sm_count = 148;
 
     int n = 0;                 // particles
@@ -239,8 +240,7 @@ int alloc_nodes(sphb_ctx * c, int cap, int keep, int keep_offs = 0)
     if (dev_alloc(c, &c->lvl_tmp, cap, c->node_allocs) || dev_alloc(c, &c->lvl_offs, cap, c->node_allocs)) return 1;
     if (keep_offs) CK(cudaMemcpyAsync(c->lvl_offs, old_offs, (size_t)keep_offs * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     TreeDev & o = c->td;
-    if (dev_alloc(c, &o.meta, cap, c->node_allocs) || dev_alloc(c, &o.geo, cap, c->node_allocs) ||
-        dev_alloc(c, &o.com, cap, c->node_allocs) || dev_alloc(c, &o.ksize, cap, c->node_allocs) ||
+    if (dev_alloc(c, &o.nn, (size_t)cap * 4, c->node_allocs) || dev_alloc(c, &o.ng, (size_t)cap * 4, c->node_allocs) ||
         dev_alloc(c, &o.parent, cap, c->node_allocs)) return 1;
     CK(cudaStreamSynchronize(c->stream));
     free_bag(old_bag);
@@ -317,6 +317,11 @@ __global__ void k_set_scalars(double * s, double dt, double hpvs, int which)
     if (which & 2) s[1] = hpvs;
 }
 
+// gather records in memory that is dead between make_tree calls (the inactive SoA side):
+// {x,y,z,m} per particle in its first four arrays, {2/h, h^2} in the next two
+double4 * posm_of(sphb_ctx * c) { return reinterpret_cast<double4 *>(c->alt.pos[0]); }
+double2 * hsoft_of(sphb_ctx * c) { return reinterpret_cast<double2 *>(c->alt.pos[0] + (size_t)4 * c->n_pad); }
+
 // ---- tree ---------------------------------------------------------------------------------------------
 template <int DIM> int make_tree_t(sphb_ctx * c)
 {
@@ -378,6 +383,7 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     }
     c->td.n_nodes = n_nodes;
     k_tree_scatter<DIM><<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, c->td, n_nodes, c->d_root); LAUNCH_CHECK();
+    k_pack_posm<DIM><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, posm_of(c), n); LAUNCH_CHECK();
     c->tree_valid = true;
     c->last_counters.tree_nodes = (uint64_t)n_nodes;
     return 0;
@@ -385,7 +391,7 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
 
 int set_kernel(sphb_ctx * c)
 {
-    CK(cudaMemsetAsync(c->td.ksize, 0, (size_t)c->td.n_nodes * sizeof(double), c->stream));
+    k_clear_kernel<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td); LAUNCH_CHECK();
     k_set_kernel<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td, c->cur.sml); LAUNCH_CHECK();
     return 0;
 }
@@ -428,7 +434,7 @@ template <int DIM, int KT, int SPH> int pre_t(sphb_ctx * c)
     if (c->first_pre) {
         // initial_smoothing needs every particle's density before the main pass: all ranks do all
         // particles (first call only)
-        k_initial_smoothing<DIM, KT><<<cdiv(cdiv(c->n, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n); LAUNCH_CHECK();
+        k_initial_smoothing<DIM, KT><<<cdiv(cdiv(c->n, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n, posm_of(c)); LAUNCH_CHECK();
         c->first_pre = false;
     }
     k_set_scalars<<<1, 1, 0, c->stream>>>(c->d_scal, 0.0, DBL_MAX, 2); LAUNCH_CHECK();
@@ -437,7 +443,7 @@ template <int DIM, int KT, int SPH> int pre_t(sphb_ctx * c)
     if (ng > 0) {
         const int grid = std::min(c->pre_grid, cdiv(ng, 4));
         k_pre_interaction<DIM, KT, SPH><<<grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n, g0 + ng, c->d_group_counter,
-            c->scratch_r, c->scratch_m, c->d_scal + 0, c->d_scal + 1, c->d_err, c->counters_on ? c->d_cnt : nullptr);
+            c->scratch_r, c->scratch_m, c->d_scal + 0, c->d_scal + 1, c->d_err, c->counters_on ? c->d_cnt : nullptr, posm_of(c));
         LAUNCH_CHECK();
     }
     if (c->world > 1) {
@@ -478,7 +484,7 @@ template <int DIM, int KT, int SPH> int force_t(sphb_ctx * c)
     const Slice s = my_slice(c);
     if (s.n_local > 0) {
         k_fluid_force<DIM, KT, SPH><<<cdiv(cdiv(s.n_local, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n,
-            s.first_particle, s.first_particle + s.n_local, c->d_scal + 0, c->counters_on ? c->d_cnt : nullptr);
+            s.first_particle, s.first_particle + s.n_local, c->d_scal + 0, c->counters_on ? c->d_cnt : nullptr, posm_of(c));
         LAUNCH_CHECK();
     }
     return 0;
@@ -508,8 +514,9 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
         return 0;
     }
     if (s.n_local > 0) {
+        k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, hsoft_of(c), c->n); LAUNCH_CHECK();
         k_gravity<DIM><<<cdiv(cdiv(s.n_local, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n,
-            s.first_particle, s.first_particle + s.n_local, c->counters_on ? c->d_cnt : nullptr);
+            s.first_particle, s.first_particle + s.n_local, posm_of(c), hsoft_of(c), c->counters_on ? c->d_cnt : nullptr);
         LAUNCH_CHECK();
     }
     return 0;
@@ -638,7 +645,8 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
     P.kernel_ratio = hp->iterative_sml ? 1.2 : 1.0;
     P.key_levels = std::max(1, std::min(hp->max_tree_level, 63 / dim));
     P.list_cap = hp->neighbor_number * 20;
-    cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    c->stream = c->own_stream;
     void * q = nullptr;
     cudaMalloc(&q, 4 * sizeof(double)); c->d_root = (double *)q;
     cudaMalloc(&q, 8 * sizeof(double)); c->d_scal = (double *)q;
@@ -676,7 +684,7 @@ void sphb_destroy(sphb_ctx * c)
     cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -685,7 +693,7 @@ const char * sphb_last_error(const sphb_ctx * c) { return c ? c->err.c_str() : g
 int sphb_set_stream(sphb_ctx * c, void * s)
 {
     cudaStreamSynchronize(c->stream);
-    c->stream = (cudaStream_t)s;      // the context's own stream is kept alive until destroy only if never replaced
+    c->stream = (cudaStream_t)s;
     return 0;
 }
 int sphb_synchronize(sphb_ctx * c) { CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return 0; }
@@ -751,7 +759,7 @@ int sphb_upload_aos(sphb_ctx * c, const void * particles, int n, size_t stride, 
     default: k_unpack<3><<<cdiv(n, 256), 256, 0, c->stream>>>((const char *)c->d_aos, rec, c->cur, n, mask, first); break;
     }
     LAUNCH_CHECK();
-    if (mask & SPHB_F_POS) c->tree_valid = false;
+    if (mask & (SPHB_F_POS | SPHB_F_MASS)) c->tree_valid = false;
     CK(cudaStreamSynchronize(c->stream));        // the caller may reuse its buffer
     return 0;
 }
@@ -967,7 +975,7 @@ int sphb_neighbor_lists(sphb_ctx * c, const double * h, int symmetric, int64_t *
     }
     if (dev_alloc(c, &d_counts, n, bag) || dev_alloc(c, &d_offs, n + 1, bag)) { free_bag(bag); return 1; }
     const int grid = cdiv(cdiv(n, 32), 4);
-#define NL(D, FILL) k_neighbor_lists<D><<<grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, n, d_h, symmetric, FILL, d_counts, d_offs, d_ids, cap_total)
+#define NL(D, FILL) k_neighbor_lists<D><<<grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, n, d_h, symmetric, FILL, d_counts, d_offs, d_ids, cap_total, posm_of(c))
     switch (c->dim) { case 1: NL(1, 0); break; case 2: NL(2, 0); break; default: NL(3, 0); break; }
     LAUNCH_CHECK();
     std::vector<int> counts(n), orig(n);
@@ -1024,10 +1032,13 @@ int sphb_get_counters(sphb_ctx * c, sphb_counters * out)
     o.pre_candidates = h.pre_candidates; o.pre_neighbors = h.pre_neighbors;
     o.force_pairs = h.force_pairs; o.grav_pp = h.grav_pp; o.grav_pc = h.grav_pc; o.grav_node_visits = h.grav_node_visits;
     if (c->tree_valid) {
-        std::vector<int4> meta(c->td.n_nodes);
-        CK(cudaMemcpy(meta.data(), c->td.meta, meta.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+        std::vector<double2> nn((size_t)c->td.n_nodes * 4);
+        CK(cudaMemcpy(nn.data(), c->td.nn, nn.size() * sizeof(double2), cudaMemcpyDeviceToHost));
         uint64_t leaves = 0;
-        for (auto & m : meta) leaves += m.w ? 1 : 0;
+        for (int k = 0; k < c->td.n_nodes; ++k) {
+            long long bits; std::memcpy(&bits, &nn[(size_t)k * 4 + 3].x, 8);
+            leaves += (bits >> 32) ? 1 : 0;
+        }
         o.tree_leaves = leaves; o.tree_nodes = (uint64_t)c->td.n_nodes;
     }
     *out = o;

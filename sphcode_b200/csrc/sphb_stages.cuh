@@ -7,8 +7,8 @@
 //   TimeStep         src/timestep.cpp:18-38
 //   predict/correct  src/solver.cpp:431-474
 // One warp owns 32 consecutive particles of the sorted order; lane = particle i.  Every sum over
-// neighbours j is a warp_walk (sphb_tree.cuh) whose leaf handler streams the leaf's particles with
-// warp-uniform loads, so there are no per-particle neighbour lists in memory at all; the only
+// neighbours j is a warp_walk (sphb_tree.cuh) whose leaf handler streams the leaf's particles from a
+// shared-memory tile, so there are no per-particle neighbour lists in memory at all; the only
 // per-lane list is the r (and m) column of the Newton iteration, which must see one fixed
 // candidate set several times (src/pre_interaction.cpp:227-283).
 #pragma once
@@ -48,32 +48,34 @@ template <int DIM> __device__ __forceinline__ double h_guess(int ngb, double mas
 // =================================================================================================
 template <int DIM, int KT>
 struct InitSmoothV {
-    const DevParams & P; const TreeDev & t; const PSoA & p;
+    const DevParams & P;
     double ri[DIM], h, h2, dens;
     KernelCoef<DIM, KT> kc;
-    __device__ __forceinline__ bool open(int idx) { return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, h); }
-    __device__ __forceinline__ void leaf(int, int first, int count)
+    __device__ __forceinline__ bool open(const NodeRec & nd) { return node_in_reach<DIM>(P, nd, ri, h); }
+    __device__ __forceinline__ void leaf(const NodeRec &, int, int m, const double4 * sl)
     {
-        for (int j = first; j < first + count; ++j) {
-            double rj[DIM], d[DIM];
-            load_vec<DIM>(p.pos, j, rj);
-            calc_r_ij<DIM>(P, ri, rj, d);
+#pragma unroll 4
+        for (int k = 0; k < m; ++k) {
+            const double4 pj = sl[k];
+            double d[DIM];
+            rij_from4<DIM>(P, ri, pj, d);
             const double r2 = abs2_exact<DIM>(d);
             if (r2 < h2) {
                 const double r = sqrt(r2);
-                if (r < h) dens += p.mass[j] * kc.w(r);
+                if (r < h) dens += pj.w * kc.w(r);
             }
         }
     }
 };
 
 template <int DIM, int KT>
-__global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, TreeDev t, DevParams P, int n)
+__global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, TreeDev t, DevParams P, int n, const double4 * __restrict__ posm)
 {
+    __shared__ double4 s_leaf[4][32];
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
     const bool valid = i < n;
-    InitSmoothV<DIM, KT> v{P, t, p};
+    InitSmoothV<DIM, KT> v{P};
     v.dens = 0.0;
     v.h = 1.0;
     if (valid) {
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, TreeDev t, De
     }
     v.h2 = __dmul_rn(v.h, v.h);
     v.kc.init(v.h);
-    warp_walk(t, v, valid);
+    warp_walk(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
     if (valid) { p.sml[i] = v.h; p.dens[i] = v.dens; }
 }
 
@@ -95,22 +97,23 @@ __global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, TreeDev t, De
 // walk 1: candidate set {j : r2 < h_search^2} (src/bhtree.cpp:251-261) -> per-lane r (and m) column
 template <int DIM, bool NEED_M>
 struct CollectV {
-    const DevParams & P; const TreeDev & t; const PSoA & p;
+    const DevParams & P;
     double ri[DIM], hs, hs2;
     double * lr; double * lm;
     int cap, cnt, lane;
-    __device__ __forceinline__ bool open(int idx) { return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, hs); }
-    __device__ __forceinline__ void leaf(int, int first, int count)
+    __device__ __forceinline__ bool open(const NodeRec & nd) { return node_in_reach<DIM>(P, nd, ri, hs); }
+    __device__ __forceinline__ void leaf(const NodeRec &, int, int m, const double4 * sl)
     {
-        for (int j = first; j < first + count; ++j) {
-            double rj[DIM], d[DIM];
-            load_vec<DIM>(p.pos, j, rj);
-            calc_r_ij<DIM>(P, ri, rj, d);
+#pragma unroll 4
+        for (int k = 0; k < m; ++k) {
+            const double4 pj = sl[k];
+            double d[DIM];
+            rij_from4<DIM>(P, ri, pj, d);
             const double r2 = abs2_exact<DIM>(d);
             if (r2 < hs2) {
                 if (cnt < cap) {
                     lr[cnt * 32 + lane] = sqrt(r2);
-                    if (NEED_M) lm[cnt * 32 + lane] = p.mass[j];
+                    if (NEED_M) lm[cnt * 32 + lane] = pj.w;
                 }
                 ++cnt;
             }
@@ -118,14 +121,20 @@ struct CollectV {
     }
 };
 
+// Leaf handlers of the heavy passes work in two stages so that the expensive pair body is not
+// executed under the (very sparse) per-particle hit predicate: stage 1 streams the leaf's particles
+// with warp-uniform loads and records a per-lane hit mask (cheap, convergent); stage 2 lets every
+// lane walk its own mask, so lanes with hits at DIFFERENT j run the pair body together (their loads
+// fall into the same one or two cache lines of the leaf's contiguous range).
+
 // walk 2: sums over {j : r2 < h_search^2 and r < h_i}: density pass + Balsara / MUSCL-gradient pass
 // (the reference runs them as two loops over the same sorted list prefix,
 //  src/pre_interaction.cpp:83-103 and 116-161; the second only needs dens_i at the very end)
 template <int DIM, int KT, int SPH>
 struct DensityV {
-    const DevParams & P; const TreeDev & t; const PSoA & p;
+    const DevParams & P; const PSoA & p;
     int i;
-    double ri[DIM], vi[DIM], hs2, h, reach, ci, ui;
+    double ri[DIM], vi[DIM], hs2, h, reach, hit2, ci, ui;   // hit2: cheap stage-1 bound >= min(hs2, h^2)
     KernelCoef<DIM, KT> kc;
     bool need_div;
     // accumulators
@@ -134,19 +143,30 @@ struct DensityV {
     double div_v, rot_v[3];
     double dd[DIM], du[DIM], dv[DIM][DIM];   // GSPH
 
-    __device__ __forceinline__ bool open(int idx) { return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, reach); }
-    __device__ __forceinline__ void leaf(int, int first, int count)
+    __device__ __forceinline__ bool open(const NodeRec & nd) { return node_in_reach<DIM>(P, nd, ri, reach); }
+    __device__ __forceinline__ void leaf(const NodeRec &, int base, int m, const double4 * sl)
     {
-        for (int j = first; j < first + count; ++j) {
-            double rj[DIM], d[DIM];
-            load_vec<DIM>(p.pos, j, rj);
-            calc_r_ij<DIM>(P, ri, rj, d);
+        unsigned hits = 0;
+#pragma unroll 4
+        for (int k = 0; k < m; ++k) {
+            double d[DIM];
+            rij_from4<DIM>(P, ri, sl[k], d);
+            const double r2 = abs2_exact<DIM>(d);
+            if (r2 < hit2) hits |= 1u << k;
+        }
+        while (hits) {
+            const int kb = __ffs(hits) - 1;
+            const int j = base + kb;
+            hits &= hits - 1;
+            const double4 pj = sl[kb];
+            double d[DIM];
+            rij_from4<DIM>(P, ri, pj, d);
             const double r2 = abs2_exact<DIM>(d);
             if (!(r2 < hs2)) continue;
             const double r = sqrt(r2);
             if (r >= h) continue;                       // the `break` of the sorted loop
             ++n_neighbor;
-            const double mj = p.mass[j];
+            const double mj = pj.w;
             const double w = kc.w(r);
             dens += mj * w;
             double uj = 0.0;
@@ -209,8 +229,10 @@ __global__ void __launch_bounds__(128)
 k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __restrict__ group_counter,
                   double * __restrict__ scratch_r, double * __restrict__ scratch_m,
                   const double * __restrict__ d_dt, double * __restrict__ d_hpvs,
-                  unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt)
+                  unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt, const double4 * __restrict__ posm)
 {
+    __shared__ double4 s_leaf_all[4][32];
+    double4 * s_leaf = s_leaf_all[threadIdx.x >> 5];
     constexpr bool NEED_M = (SPH != T_DISPH);     // DISPH Newton uses unit weights (d_pre_interaction.cpp:208-209)
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -218,7 +240,7 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
     double * lm = NEED_M ? scratch_m + (size_t)slot * P.list_cap * 32 : nullptr;
     const double dt = *d_dt;
     double hpvs_min = 1.7976931348623157e308;
-    unsigned long long c_evals = 0, c_iters = 0, c_cand = 0, c_ngb = 0, c_nonconv = 0, c_over = 0;
+    unsigned int c_evals = 0, c_iters = 0, c_cand = 0, c_ngb = 0, c_nonconv = 0, c_over = 0;   // per lane: fits 32 bits
 
     for (;;) {
         int g = 0;
@@ -244,11 +266,11 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
 
         if (P.iterative) {
             // ---- walk 1: candidates
-            CollectV<DIM, NEED_M> cv{P, t, p};
+            CollectV<DIM, NEED_M> cv{P};
 #pragma unroll
             for (int d = 0; d < DIM; ++d) cv.ri[d] = ri[d];
             cv.hs = hs; cv.hs2 = hs2; cv.lr = lr; cv.lm = lm; cv.cap = P.list_cap; cv.cnt = 0; cv.lane = lane;
-            warp_walk(t, cv, valid);
+            warp_walk(t, posm, s_leaf, lane, cv, valid);
             int ncand = cv.cnt;
             if (ncand > P.list_cap) { ++c_over; ncand = P.list_cap; }
             c_cand += valid ? ncand : 0;
@@ -291,11 +313,12 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
         }
 
         // ---- walk 2: density pass (+ Balsara / MUSCL gradients)
-        DensityV<DIM, KT, SPH> dv{P, t, p};
+        DensityV<DIM, KT, SPH> dv{P, p};
         dv.i = i;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) { dv.ri[d] = ri[d]; dv.vi[d] = vi[d]; }
         dv.hs2 = hs2; dv.h = h; dv.reach = fmin(h, hs); dv.ci = c_i; dv.ui = ene_i;
+        dv.hit2 = fmin(hs2, h * h * (1.0 + 1e-14));
         dv.kc.init(h);
         dv.need_div = (SPH != T_GSPH) && ((P.use_balsara && DIM != 1) || P.use_tdav);
         dv.dens = dv.dh_dens = dv.n_i = dv.dh_n = dv.pres = dv.dh_pres = 0.0;
@@ -308,7 +331,7 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
 #pragma unroll
             for (int k = 0; k < DIM; ++k) dv.dv[k][a] = 0.0;
         }
-        warp_walk(t, dv, valid);
+        warp_walk(t, posm, s_leaf, lane, dv, valid);
 
         if (valid) {
             const double dens_i = dv.dens;
@@ -372,19 +395,17 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
     hpvs_min = warp_min(hpvs_min);
     if (lane == 0) atomic_min_pos(d_hpvs, hpvs_min);
     if (cnt) {
-        c_evals = warp_sum_u64(c_evals); c_iters = warp_sum_u64(c_iters); c_cand = warp_sum_u64(c_cand);
-        c_ngb = warp_sum_u64(c_ngb);
-    }
-    c_nonconv = warp_sum_u64(c_nonconv); c_over = warp_sum_u64(c_over);
-    if (lane == 0) {
-        if (cnt) {
-            atomicAdd(&cnt->newton_evals, c_evals); atomicAdd(&cnt->newton_iters, c_iters);
-            atomicAdd(&cnt->pre_candidates, c_cand); atomicAdd(&cnt->pre_neighbors, c_ngb);
+        const unsigned long long e = warp_sum_u64(c_evals), it = warp_sum_u64(c_iters), ca = warp_sum_u64(c_cand),
+                                 ng = warp_sum_u64(c_ngb);
+        if (lane == 0) {
+            atomicAdd(&cnt->newton_evals, e); atomicAdd(&cnt->newton_iters, it);
+            atomicAdd(&cnt->pre_candidates, ca); atomicAdd(&cnt->pre_neighbors, ng);
         }
     }
-    if (lane == 0 && (c_nonconv | c_over)) {      // always-on error counters
-        atomicAdd(&d_err[0], c_nonconv);
-        atomicAdd(&d_err[1], c_over);
+    const unsigned long long nc = warp_sum_u64(c_nonconv), ov = warp_sum_u64(c_over);
+    if (lane == 0 && (nc | ov)) {      // always-on error counters
+        atomicAdd(&d_err[0], nc);
+        atomicAdd(&d_err[1], ov);
     }
 }
 
@@ -437,7 +458,7 @@ __device__ __forceinline__ void hll(const double (&left)[4], const double (&righ
 
 template <int DIM, int KT, int SPH>
 struct ForceV {
-    const DevParams & P; const TreeDev & t; const PSoA & p;
+    const DevParams & P; const PSoA & p;
     int i;
     double dt;
     double ri[DIM], vi[DIM], h_i, m_i, dens_i, pres_i, gradh_i, alpha_i, bal_i, c_i, u_i;
@@ -447,23 +468,33 @@ struct ForceV {
     double m_u_inv;         // DISPH: 1/(m_i u_i)
     KernelCoef<DIM, KT> ki;
     double acc[DIM], dene;
-    unsigned long long pairs;
+    unsigned int pairs;
 
-    __device__ __forceinline__ bool open(int idx)
+    __device__ __forceinline__ bool open(const NodeRec & nd)
     {
-        const double h = fmax(h_i, __ldg(&t.ksize[idx]));           // src/bhtree.cpp:237
-        return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, h);
+        const double h = fmax(h_i, nd.e);                           // src/bhtree.cpp:237
+        return node_in_reach<DIM>(P, nd, ri, h);
     }
-    __device__ __forceinline__ void leaf(int idx, int first, int count)
+    __device__ __forceinline__ void leaf(const NodeRec & nd, int base, int m, const double4 * sl)
     {
-        const double h = fmax(h_i, __ldg(&t.ksize[idx]));
+        const double h = fmax(h_i, nd.e);
         const double h2 = __dmul_rn(h, h);
-        for (int j = first; j < first + count; ++j) {
-            double rj[DIM], d[DIM];
-            load_vec<DIM>(p.pos, j, rj);
-            calc_r_ij<DIM>(P, ri, rj, d);
+        unsigned hits = 0;
+#pragma unroll 4
+        for (int k = 0; k < m; ++k) {
+            double d[DIM];
+            rij_from4<DIM>(P, ri, sl[k], d);
             const double r2 = abs2_exact<DIM>(d);
-            if (!(r2 < h2)) continue;                               // src/bhtree.cpp:255-256
+            if (r2 < h2) hits |= 1u << k;                           // src/bhtree.cpp:255-256
+        }
+        while (hits) {
+            const int kb = __ffs(hits) - 1;
+            const int j = base + kb;
+            hits &= hits - 1;
+            const double4 pj = sl[kb];
+            double d[DIM];
+            rij_from4<DIM>(P, ri, pj, d);
+            const double r2 = abs2_exact<DIM>(d);
             const double h_j = p.sml[j];
             const double r = sqrt(r2);
             if (r >= fmax(h_i, h_j) || r == 0.0) continue;          // src/fluid_force.cpp:62
@@ -475,7 +506,7 @@ struct ForceV {
             load_vec<DIM>(p.vel, j, vj);
 #pragma unroll
             for (int a = 0; a < DIM; ++a) { dw_i[a] = d[a] * cwi; dw_j[a] = d[a] * cwj; vij[a] = vi[a] - vj[a]; }
-            const double m_j = p.mass[j];
+            const double m_j = pj.w;
             const double dens_j = p.dens[j], pres_j = p.pres[j];
 
             if (SPH == T_GSPH) {
@@ -575,12 +606,13 @@ struct ForceV {
 template <int DIM, int KT, int SPH>
 __global__ void __launch_bounds__(128)
 k_fluid_force(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const double * __restrict__ d_dt,
-              Counters * __restrict__ cnt)
+              Counters * __restrict__ cnt, const double4 * __restrict__ posm)
 {
+    __shared__ double4 s_leaf[4][32];
     const int lane = threadIdx.x & 31;
     const int i = i_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
     const bool valid = i < i_end;
-    ForceV<DIM, KT, SPH> v{P, t, p};
+    ForceV<DIM, KT, SPH> v{P, p};
     v.i = i;
     v.dt = *d_dt;
     v.pairs = 0;
@@ -613,14 +645,14 @@ k_fluid_force(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, con
         v.pp_i = 1.0 / (v.dens_i * v.dens_i);
     }
     v.ki.init(v.h_i);
-    warp_walk(t, v, valid);
+    warp_walk(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
     if (valid) {
 #pragma unroll
         for (int a = 0; a < DIM; ++a) p.acc[a][i] = v.acc[a];
         p.dene[i] = v.dene;
     }
     if (cnt) {
-        const unsigned long long s = warp_sum_u64(valid ? v.pairs : 0ull);
+        const unsigned long long s = warp_sum_u64(valid ? (unsigned long long)v.pairs : 0ull);
         if (lane == 0) atomicAdd(&cnt->force_pairs, s);
     }
 }
@@ -628,88 +660,210 @@ k_fluid_force(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, con
 // =================================================================================================
 // GravityForce::calculation -> BHNode::calc_force, src/bhtree.cpp:301-331
 // =================================================================================================
-template <int DIM>
-struct GravityV {
-    const DevParams & P; const TreeDev & t; const PSoA & p;
-    double ri[DIM], h_i, einv_i, acc[DIM], phi;
-    unsigned long long n_pp, n_pc, n_visit;
+// The walk visits the union of the 32 lanes' reference walks; each lane applies the reference's own
+// opening test (edge^2 > theta^2 |r_i - com|^2) to the nodes it is still descending, so the set of
+// cells it accepts and leaves it opens is exactly BHNode::calc_force's for that particle.  The
+// interactions themselves are deferred so that lanes do them together although they accept /
+// open at different nodes:
+//   * accepted cells go to a 32-entry chunk staged in shared memory (mass centre + mass) with a
+//     per-lane accept mask; when the chunk is full every lane runs over ITS mask (popcounts are
+//     close, so the monopole body runs convergent);
+//   * opened leaves go to a per-lane queue of (first, count); when any lane's queue is full, every
+//     lane runs one flattened loop over all particles of its queued leaves (packed x,y,z,m + 2/h
+//     read through L1; lanes of a warp are Morton neighbours and share these lines).
+constexpr int GRAV_LQ = 8;      // leaf queue depth per lane
 
-    __device__ __forceinline__ bool open(int idx)
-    {
-        ++n_visit;
-        const double4 c = ldg4(&t.com[idx]);
-        const double edge = ldg4(&t.geo[idx]).w;
-        double cm[DIM], d[DIM];
-        cm[0] = c.x;
-        if (DIM >= 2) cm[DIM >= 2 ? 1 : 0] = c.y;
-        if (DIM >= 3) cm[DIM >= 3 ? 2 : 0] = c.z;
-        calc_r_ij<DIM>(P, ri, cm, d);
-        const double d2 = abs2_exact<DIM>(d);
-        const double l2 = __dmul_rn(edge, edge);
-        if (l2 > __dmul_rn(P.theta2, d2)) return true;
-        // monopole, src/bhtree.cpp:326-330
-        const double r_inv = 1.0 / sqrt(d2);
-        const double gm = P.G * c.w;
-        phi -= gm * r_inv;
-        const double s = gm * (r_inv * r_inv * r_inv);
-#pragma unroll
-        for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
-        ++n_pc;
-        return false;
+// Softening functions with the divisions by constants turned into products (soft_fg in
+// sphb_math.cuh keeps the literal form for the direct-sum checker kernel).
+__device__ __forceinline__ void soft_fg_fast(double r, double rinv, double einv, double & f, double & g)
+{
+    const double u = r * einv;
+    if (u < 1.0) {
+        const double u2 = u * u;
+        f = (-0.5 * u2 * (1.0 / 3.0 - (3.0 / 20) * u2 + (1.0 / 20) * (u2 * u)) + 1.4) * einv;
+        g = (4.0 / 3.0 - 1.2 * u2 + 0.5 * (u2 * u)) * (einv * einv * einv);
+    } else if (u < 2.0) {
+        const double u2 = u * u, u3 = u2 * u;
+        f = (-1.0 / 15) * rinv + (-u2 * (4.0 / 3.0 - u + 0.3 * u2 - (1.0 / 30) * u3) + 1.6) * einv;
+        g = (-1.0 / 15 + (8.0 / 3) * u3 - 3 * (u3 * u) + 1.2 * (u3 * u2) - (1.0 / 6.0) * (u3 * u3)) * (rinv * rinv * rinv);
+    } else {
+        f = rinv;
+        g = rinv * rinv * rinv;
     }
-    __device__ __forceinline__ void leaf(int, int first, int count)
-    {
-        for (int j = first; j < first + count; ++j) {
-            double rj[DIM], d[DIM];
-            load_vec<DIM>(p.pos, j, rj);
-            calc_r_ij<DIM>(P, ri, rj, d);
-            const double r2 = abs2_exact<DIM>(d);
-            const double r = sqrt(r2);
-            const double rinv = 1.0 / r;               // inf at r == 0, unused there (u < 1 branch)
-            const double einv_j = 2.0 / p.sml[j];
-            double fi, gi, fj, gj;
-            soft_fg(r, rinv, einv_i, fi, gi);
-            soft_fg(r, rinv, einv_j, fj, gj);
-            const double gm = P.G * p.mass[j];
-            phi -= gm * (fi + fj) * 0.5;
-            const double s = gm * (gi + gj) * 0.5;
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
-            ++n_pp;
-        }
-    }
-};
+}
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, Counters * __restrict__ cnt)
+k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const double4 * __restrict__ posm,
+          const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, Counters * __restrict__ cnt)
 {
-    const int lane = threadIdx.x & 31;
-    const int i = i_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+    __shared__ double4 s_pc[4][32];
+    __shared__ int2 s_lq[4][GRAV_LQ][32];
+    __shared__ unsigned s_near[4][GRAV_LQ][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = i_begin + (blockIdx.x * (blockDim.x >> 5) + w) * 32 + lane;
     const bool valid = i < i_end;
-    GravityV<DIM> v{P, t, p};
-    v.n_pp = v.n_pc = v.n_visit = 0;
-    v.phi = 0.0;                                    // src/bhtree.cpp:130
-    v.h_i = 1.0;
+    double ri[DIM], acc[DIM], phi = 0.0, h_i = 1.0;          // phi = 0: src/bhtree.cpp:130
 #pragma unroll
-    for (int a = 0; a < DIM; ++a) { v.ri[a] = 0.0; v.acc[a] = 0.0; }
+    for (int a = 0; a < DIM; ++a) { ri[a] = 0.0; acc[a] = 0.0; }
     if (valid) {
-        load_vec<DIM>(p.pos, i, v.ri);
-        load_vec<DIM>(p.acc, i, v.acc);             // gravity adds onto the fluid acceleration
-        v.h_i = p.sml[i];
+        load_vec<DIM>(p.pos, i, ri);
+        load_vec<DIM>(p.acc, i, acc);                         // gravity adds onto the fluid acceleration
+        h_i = p.sml[i];
     }
-    v.einv_i = 2.0 / v.h_i;
-    warp_walk(t, v, valid);
+    const double einv_i = 2.0 / h_i;
+    const double h_i2 = h_i * h_i;
+    unsigned int n_pp = 0, n_pc = 0, n_visit = 0;             // per lane: fit 32 bits
+    unsigned pc_mask = 0;
+    int npc = 0, nlq = 0;
+    double4 * const my_pc = s_pc[w];
+
+    // accepted cells of the current chunk: monopole, src/bhtree.cpp:326-330
+    auto flush_pc = [&]() {
+        __syncwarp();
+        unsigned mm = pc_mask;
+        while (mm) {
+            const int e = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const double4 c = my_pc[e];
+            double d[DIM];
+            rij_from4<DIM>(P, ri, c, d);
+            const double d2 = dot<DIM>(d, d);
+            const double r_inv = rsqrt(d2);
+            const double gm = P.G * c.w;
+            phi -= gm * r_inv;
+            const double s = gm * (r_inv * r_inv * r_inv);
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
+            ++n_pc;
+        }
+        pc_mask = 0;
+        npc = 0;
+        __syncwarp();
+    };
+    // queued leaves: particle-particle sums of src/bhtree.cpp:309-317.  Pass 1 runs one flattened
+    // loop over all particles of the lane's queued leaves with the unsoftened form (u >= 2 for both
+    // h_i and h_j, i.e. r >= max(h_i, h_j)) and only MARKS the softened pairs; pass 2 runs the full
+    // Hernquist-Katz form over the marked pairs.  Both bodies run convergent across lanes.
+    auto flush_pp = [&]() {
+        int q = 0, k = 0;
+        int2 cur = make_int2(0, 0);
+        unsigned near = 0;
+        if (nlq > 0) cur = s_lq[w][0][lane];
+        while (q < nlq) {
+            const int j = cur.x + k;
+            const double4 pj = ldg4(&posm[j]);
+            const double hj2 = __ldg(&hsoft[j]).y;
+            double d[DIM];
+            rij_from4<DIM>(P, ri, pj, d);
+            const double r2 = dot<DIM>(d, d);
+            if (r2 < fmax(h_i2, hj2) * (1.0 + 1e-12)) {
+                near |= 1u << k;
+            } else {
+                const double rinv = rsqrt(r2);
+                const double gm = P.G * pj.w;
+                phi -= gm * rinv;
+                const double s = gm * (rinv * rinv * rinv);
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
+            }
+            ++n_pp;
+            if (++k == cur.y) {
+                s_near[w][q][lane] = near;
+                near = 0;
+                k = 0;
+                ++q;
+                if (q < nlq) cur = s_lq[w][q][lane];
+            }
+        }
+        q = 0;
+        near = 0;
+        int first = 0;
+        for (;;) {
+            while (near == 0 && q < nlq) { near = s_near[w][q][lane]; first = s_lq[w][q][lane].x; ++q; }
+            if (near == 0) break;
+            const int j = first + __ffs(near) - 1;
+            near &= near - 1;
+            const double4 pj = ldg4(&posm[j]);
+            const double einv_j = __ldg(&hsoft[j]).x;
+            double d[DIM];
+            rij_from4<DIM>(P, ri, pj, d);
+            const double r2 = dot<DIM>(d, d);
+            const double rinv = rsqrt(r2);              // inf at r == 0, unused there (u < 1 branch)
+            const double r = r2 > 0.0 ? r2 * rinv : 0.0;
+            double fi, gi, fj, gj;
+            soft_fg_fast(r, rinv, einv_i, fi, gi);
+            soft_fg_fast(r, rinv, einv_j, fj, gj);
+            const double gm = P.G * pj.w;
+            phi -= gm * (fi + fj) * 0.5;                // src/bhtree.cpp:314-315
+            const double s = gm * (gi + gj) * 0.5;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
+        }
+        nlq = 0;
+    };
+
+    int idx = 0;
+    int resume = valid ? 0 : INT_MAX;
+    const int n_nodes = t.n_nodes;
+    while (idx < n_nodes) {
+        const NodeRec nd = load_node(t.ng, idx);          // x,y,z = mass centre, w = mass, e = edge^2
+        bool open = false, accept = false;
+        if (idx >= resume) {
+            ++n_visit;
+            double c[DIM], d[DIM];
+            c[0] = nd.x;
+            if (DIM >= 2) c[DIM >= 2 ? 1 : 0] = nd.y;
+            if (DIM >= 3) c[DIM >= 3 ? 2 : 0] = nd.z;
+            calc_r_ij<DIM>(P, ri, c, d);
+            const double d2 = abs2_exact<DIM>(d);
+            if (nd.e > __dmul_rn(P.theta2, d2)) open = true;           // src/bhtree.cpp:308
+            else { accept = true; resume = idx + nd.skip; }
+        }
+        const unsigned acc_b = __ballot_sync(SPHB_FULL_MASK, accept);
+        const bool any_open = __any_sync(SPHB_FULL_MASK, open);
+        if (acc_b) {
+            if (accept) pc_mask |= 1u << npc;
+            if (lane == 0) my_pc[npc] = make_double4(nd.x, nd.y, nd.z, nd.w);      // node record is warp-uniform
+            if (++npc == 32) flush_pc();
+        }
+        if (any_open) {
+            if (nd.leaf) {
+                // leaves deeper than 32 particles (max tree level) are queued in 32-particle pieces
+                const int last = nd.first + nd.count;
+                for (int base = nd.first; base < last; base += 32) {
+                    if (open) { s_lq[w][nlq][lane] = make_int2(base, min(32, last - base)); ++nlq; }
+                    if (__any_sync(SPHB_FULL_MASK, nlq == GRAV_LQ)) flush_pp();
+                }
+            }
+            idx += 1;
+        } else {
+            idx += nd.skip;
+        }
+    }
+    flush_pc();
+    flush_pp();
+
     if (valid) {
 #pragma unroll
-        for (int a = 0; a < DIM; ++a) p.acc[a][i] = v.acc[a];
-        p.phi[i] = v.phi;
+        for (int a = 0; a < DIM; ++a) p.acc[a][i] = acc[a];
+        p.phi[i] = phi;
     }
     if (cnt) {
-        const unsigned long long a = warp_sum_u64(valid ? v.n_pp : 0ull), b = warp_sum_u64(valid ? v.n_pc : 0ull),
-                                 c = warp_sum_u64(valid ? v.n_visit : 0ull);
-        if (lane == 0) { atomicAdd(&cnt->grav_pp, a); atomicAdd(&cnt->grav_pc, b); atomicAdd(&cnt->grav_node_visits, c); }
+        const unsigned long long a = warp_sum_u64(valid ? (unsigned long long)n_pp : 0ull),
+                                 b = warp_sum_u64(valid ? (unsigned long long)n_pc : 0ull),
+                                 cc = warp_sum_u64(valid ? (unsigned long long)n_visit : 0ull);
+        if (lane == 0) { atomicAdd(&cnt->grav_pp, a); atomicAdd(&cnt->grav_pc, b); atomicAdd(&cnt->grav_node_visits, cc); }
     }
+}
+
+// per-particle softening record of the gravity particle-particle loop: {2 / h, h^2}
+__global__ void k_grav_pack(const double * __restrict__ sml, double2 * __restrict__ hsoft, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double h = sml[i];
+    hsoft[i] = make_double2(2.0 / h, h * h);
 }
 
 // Direct sum, the EXHAUSTIVE_SEARCH flavour of GravityForce (src/gravity_force.cpp:70-84).
@@ -859,23 +1013,23 @@ __global__ void k_energy(PSoA p, int n, double * __restrict__ out)
 // =================================================================================================
 template <int DIM>
 struct ListV {
-    const DevParams & P; const TreeDev & t; const PSoA & p;
+    const DevParams & P; const PSoA & p;
     double ri[DIM], h_i, h_i2;
     bool symmetric, fill;
     int cnt;
     int * out;           // fill: write p.orig[j] at out[cnt]
     long long cap_left;
-    __device__ __forceinline__ bool open(int idx)
+    __device__ __forceinline__ bool open(const NodeRec & nd)
     {
-        const double h = symmetric ? fmax(h_i, __ldg(&t.ksize[idx])) : h_i;
-        return node_in_reach<DIM>(P, ldg4(&t.geo[idx]), ri, h);
+        const double h = symmetric ? fmax(h_i, nd.e) : h_i;
+        return node_in_reach<DIM>(P, nd, ri, h);
     }
-    __device__ __forceinline__ void leaf(int, int first, int count)
+    __device__ __forceinline__ void leaf(const NodeRec &, int base, int m, const double4 * sl)
     {
-        for (int j = first; j < first + count; ++j) {
-            double rj[DIM], d[DIM];
-            load_vec<DIM>(p.pos, j, rj);
-            calc_r_ij<DIM>(P, ri, rj, d);
+        for (int k = 0; k < m; ++k) {
+            const int j = base + k;
+            double d[DIM];
+            rij_from4<DIM>(P, ri, sl[k], d);
             const double r2 = abs2_exact<DIM>(d);
             double k2 = h_i2;
             if (symmetric) { const double hj = p.sml[j]; k2 = fmax(h_i2, __dmul_rn(hj, hj)); }   // exhaustive_search.cpp:28
@@ -891,12 +1045,13 @@ template <int DIM>
 __global__ void __launch_bounds__(128)
 k_neighbor_lists(PSoA p, TreeDev t, DevParams P, int n, const double * __restrict__ h_override /* sorted order or null */,
                  int symmetric, int fill, int * __restrict__ counts, const long long * __restrict__ offsets,
-                 int * __restrict__ ids, long long cap_total)
+                 int * __restrict__ ids, long long cap_total, const double4 * __restrict__ posm)
 {
+    __shared__ double4 s_leaf[4][32];
     const int lane = threadIdx.x & 31;
     const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
     const bool valid = i < n;
-    ListV<DIM> v{P, t, p};
+    ListV<DIM> v{P, p};
     v.symmetric = symmetric != 0; v.fill = fill != 0; v.cnt = 0; v.out = nullptr; v.cap_left = 0;
     v.h_i = 1.0;
 #pragma unroll
@@ -911,7 +1066,7 @@ k_neighbor_lists(PSoA p, TreeDev t, DevParams P, int n, const double * __restric
         }
     }
     v.h_i2 = __dmul_rn(v.h_i, v.h_i);
-    warp_walk(t, v, valid);
+    warp_walk(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
     if (valid && !fill) counts[i] = v.cnt;
 }
 

@@ -40,15 +40,30 @@ struct TreeBuild {
     double *msum, *mpos[3];
 };
 
-// Finished tree, DFS pre-order.  meta = {skip, first, count, is_leaf}.
+// Finished tree, DFS pre-order, one packed 64-byte record (4 x double2) per node and walk kind so
+// that a node visit is four 16-byte warp-uniform loads off one address:
+//   nn (neighbour walks): [0] cx, cy   [1] cz, edge   [2] ksize, {skip, first}   [3] {count, leaf}, -
+//   ng (gravity walk):    [0] mx, my   [1] mz, mass   [2] edge^2, {skip, first}  [3] {count, leaf}, -
+// (c = geometric centre, m = mass centre, ksize = BHNode::kernel_size set by set_kernel,
+//  skip = nodes in the subtree incl. this one, first/count = particle range, leaf = is_leaf)
 struct TreeDev {
-    int     n_nodes;
-    int4   *meta;
-    double4 *geo;       // geometric centre x,y,z + edge          (neighbour search)
-    double4 *com;       // mass centre x,y,z + mass               (gravity)
-    double  *ksize;     // BHNode::kernel_size, set by set_kernel (symmetric search)
+    int      n_nodes;
+    double2 *nn;
+    double2 *ng;
     int     *parent;    // DFS index of the parent, -1 for the root
 };
+struct NodeRec { double x, y, z, w, e; int skip, first, count, leaf; };
+__device__ __forceinline__ NodeRec load_node(const double2 * __restrict__ base, int idx)
+{
+    const double2 * q = base + (size_t)idx * 4;
+    const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+    NodeRec r;
+    r.x = q0.x; r.y = q0.y; r.z = q1.x; r.w = q1.y; r.e = q2.x;
+    r.skip = __double2loint(q2.y); r.first = __double2hiint(q2.y);
+    r.count = __double2loint(q3.x); r.leaf = __double2hiint(q3.x);
+    return r;
+}
+__device__ __forceinline__ double * node_ksize(const TreeDev & t, int idx) { return &t.nn[(size_t)idx * 4 + 2].x; }
 
 // root[0..2] = centre, root[3] = edge.
 // ---- bounding cube: BHTree::make, src/bhtree.cpp:59-95 -----------------------------------------
@@ -295,7 +310,6 @@ __global__ void k_tree_scatter(TreeBuild t, TreeDev o, int n_nodes, const double
     if (i >= n_nodes) return;
     const int D = t.dfs[i];
     const int level = t.level[i];
-    o.meta[D] = make_int4(t.size[i], t.first[i], t.count[i], t.nchild[i] == 0 ? 1 : 0);
     double c[3] = {0.0, 0.0, 0.0}, mc[3] = {0.0, 0.0, 0.0};
     double m = 0.0;
 #pragma unroll
@@ -307,59 +321,97 @@ __global__ void k_tree_scatter(TreeBuild t, TreeDev o, int n_nodes, const double
 #pragma unroll
         for (int d = 0; d < DIM; ++d) mc[d] = t.mpos[d][i] / m;       // src/bhtree.cpp:152
     }
-    o.geo[D] = make_double4(c[0], c[1], c[2], ldexp(root[3], -(level - 1)));
-    o.com[D] = make_double4(mc[0], mc[1], mc[2], m);
+    const double edge = ldexp(root[3], -(level - 1));
+    const double sf = __hiloint2double(t.first[i], t.size[i]);                 // {skip, first}
+    const double cl = __hiloint2double(t.nchild[i] == 0 ? 1 : 0, t.count[i]);  // {count, leaf}
+    double2 * nn = o.nn + (size_t)D * 4;
+    nn[0] = make_double2(c[0], c[1]); nn[1] = make_double2(c[2], edge);
+    nn[2] = make_double2(0.0, sf);    nn[3] = make_double2(cl, 0.0);
+    double2 * ng = o.ng + (size_t)D * 4;
+    ng[0] = make_double2(mc[0], mc[1]); ng[1] = make_double2(mc[2], m);
+    ng[2] = make_double2(__dmul_rn(edge, edge), sf); ng[3] = make_double2(cl, 0.0);
     o.parent[D] = (i == 0) ? -1 : t.dfs[t.parent[i]];
-    o.ksize[D] = 0.0;
+}
+
+// packed {x, y, z, m} gather records of the particles (tree order), rebuilt by every make_tree
+template <int DIM>
+__global__ void k_pack_posm(PSoA p, double4 * __restrict__ posm, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = p.pos[0][i];
+    const double y = DIM >= 2 ? p.pos[DIM >= 2 ? 1 : 0][i] : 0.0;
+    const double z = DIM >= 3 ? p.pos[DIM >= 3 ? 2 : 0][i] : 0.0;
+    posm[i] = make_double4(x, y, z, p.mass[i]);
 }
 
 // BHNode::set_kernel (src/bhtree.cpp:206-232): per node the largest sml beneath it.
+__global__ void k_clear_kernel(TreeDev t)
+{
+    const int D = blockIdx.x * blockDim.x + threadIdx.x;
+    if (D < t.n_nodes) *node_ksize(t, D) = 0.0;
+}
 __global__ void k_set_kernel(TreeDev t, const double * __restrict__ sml)
 {
     const int D = blockIdx.x * blockDim.x + threadIdx.x;
     if (D >= t.n_nodes) return;
-    const int4 m = t.meta[D];
-    if (!m.w) return;
+    const double2 q2 = t.nn[(size_t)D * 4 + 2], q3 = t.nn[(size_t)D * 4 + 3];
+    if (!__double2hiint(q3.x)) return;
+    const int first = __double2hiint(q2.y), count = __double2loint(q3.x);
     double h = 0.0;
-    for (int j = m.y; j < m.y + m.z; ++j) { const double s = sml[j]; if (s > h) h = s; }
+    for (int j = first; j < first + count; ++j) { const double s = sml[j]; if (s > h) h = s; }
     const unsigned long long hb = (unsigned long long)__double_as_longlong(h);
     int q = D;
     while (q >= 0) {
-        const unsigned long long old = atomic_max_pos(&t.ksize[q], h);
+        const unsigned long long old = atomic_max_pos(node_ksize(t, q), h);
         if (old >= hb) break;          // whoever wrote `old` carries it (or more) upward
         q = t.parent[q];
     }
 }
 
 // ---- the stackless warp walk ----------------------------------------------------------------------
-// V provides   bool open(int node)                  lane criterion (may also consume the node)
-//              void leaf(int node, int first, int count)   lane opened this leaf
+// A warp of 32 consecutive particles visits the union of its lanes' reference walks.
+// V provides   bool open(const NodeRec &)                          the lane's own criterion
+//              void leaf(const NodeRec &, int base, int m, const double4 * s)
+//                   the lane opened this leaf; s[0..m) = {x,y,z,m} of particles base .. base+m-1,
+//                   staged in shared memory by one coalesced load of the whole warp.
 template <class V>
-__device__ __forceinline__ void warp_walk(const TreeDev & t, V & v, bool lane_valid)
+__device__ __forceinline__ void warp_walk(const TreeDev & t, const double4 * __restrict__ posm, double4 * s_leaf,
+                                          int lane, V & v, bool lane_valid)
 {
     int idx = 0;
     int resume = lane_valid ? 0 : INT_MAX;       // lane takes part iff idx >= resume
     const int n_nodes = t.n_nodes;
     while (idx < n_nodes) {
-        const int4 m = __ldg(&t.meta[idx]);
+        const NodeRec nd = load_node(t.nn, idx);
         bool open = false;
         if (idx >= resume) {
-            open = v.open(idx);
-            if (!open) resume = idx + m.x;
+            open = v.open(nd);
+            if (!open) resume = idx + nd.skip;
         }
         if (__any_sync(SPHB_FULL_MASK, open)) {
-            if (m.w) { if (open) v.leaf(idx, m.y, m.z); }
+            if (nd.leaf) {
+                const int last = nd.first + nd.count;
+                for (int base = nd.first; base < last; base += 32) {
+                    const int m = min(32, last - base);
+                    __syncwarp();
+                    if (lane < m) s_leaf[lane] = ldg4(&posm[base + lane]);
+                    __syncwarp();
+                    if (open) v.leaf(nd, base, m, s_leaf);
+                }
+            }
             idx += 1;
         } else {
-            idx += m.x;
+            idx += nd.skip;
         }
     }
+    __syncwarp();
 }
 
 // Per-lane neighbour criterion of BHNode::neighbor_search (src/bhtree.cpp:236-249):
 // Chebyshev minimum-image distance to the geometric centre <= edge/2 + h.
 template <int DIM>
-__device__ __forceinline__ bool node_in_reach(const DevParams & P, const double4 g, const double (&ri)[DIM], double h)
+__device__ __forceinline__ bool node_in_reach(const DevParams & P, const NodeRec & g, const double (&ri)[DIM], double h)
 {
     const double l2 = (g.w * 0.5 + h) * (g.w * 0.5 + h);
     double c[DIM];
@@ -375,6 +427,19 @@ __device__ __forceinline__ bool node_in_reach(const DevParams & P, const double4
         if (dx2 > dx2_max) dx2_max = dx2;
     }
     return dx2_max <= l2;
+}
+
+// r_ij = r_i - {x,y,z of a staged particle}, minimum image if periodic
+template <int DIM>
+__device__ __forceinline__ void rij_from4(const DevParams & P, const double (&ri)[DIM], const double4 & pj, double (&d)[DIM])
+{
+    d[0] = ri[0] - pj.x;
+    if (DIM >= 2) d[DIM >= 2 ? 1 : 0] = ri[DIM >= 2 ? 1 : 0] - pj.y;
+    if (DIM >= 3) d[DIM >= 3 ? 2 : 0] = ri[DIM >= 3 ? 2 : 0] - pj.z;
+    if (P.periodic) {
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) d[a] = min_image(d[a], P.range[a]);
+    }
 }
 
 } // namespace sphb
