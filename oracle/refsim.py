@@ -213,7 +213,7 @@ class RefSim:
         self._f["energy"](self._c, out.ctypes.data)
         return out
 
-    def neighbor_lists(self, h=None, symmetric=False, cap_total=None):
+    def neighbor_lists(self, h=None, symmetric=False, cap_total=None, exhaustive=False):
         """CSR (offsets, ids) of every particle's list; each list sorted by id (the reference
         order — by r2, unstable among ties — is not canonical)."""
         n = self.n
@@ -224,9 +224,10 @@ class RefSim:
         if h is not None:
             h = np.ascontiguousarray(h, dtype=np.float64)
             hp = h.ctypes.data
-        tot = self._f["neighbor_search_all"](self._c, hp, int(symmetric), offsets.ctypes.data, ids.ctypes.data, cap_total)
+        flags = int(symmetric) | (2 if (exhaustive and self.flavour == "port") else 0)   # port: bit 1 = brute force
+        tot = self._f["neighbor_search_all"](self._c, hp, flags, offsets.ctypes.data, ids.ctypes.data, cap_total)
         if tot > cap_total:
-            return self.neighbor_lists(h, symmetric, cap_total=int(tot))
+            return self.neighbor_lists(h, symmetric, cap_total=int(tot), exhaustive=exhaustive)
         ids = ids[:tot]
         rows = np.repeat(np.arange(n), np.diff(offsets))
         ids = ids[np.lexsort((ids, rows))]

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, TreeDev t, De
     }
     v.h2 = __dmul_rn(v.h, v.h);
     v.kc.init(v.h);
-    warp_walk(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
+    warp_walk<true>(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
     if (valid) { p.sml[i] = v.h; p.dens[i] = v.dens; }
 }
 
@@ -270,7 +270,7 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
 #pragma unroll
             for (int d = 0; d < DIM; ++d) cv.ri[d] = ri[d];
             cv.hs = hs; cv.hs2 = hs2; cv.lr = lr; cv.lm = lm; cv.cap = P.list_cap; cv.cnt = 0; cv.lane = lane;
-            warp_walk(t, posm, s_leaf, lane, cv, valid);
+            warp_walk<true>(t, posm, s_leaf, lane, cv, valid);
             int ncand = cv.cnt;
             if (ncand > P.list_cap) { ++c_over; ncand = P.list_cap; }
             c_cand += valid ? ncand : 0;
@@ -331,7 +331,7 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
 #pragma unroll
             for (int k = 0; k < DIM; ++k) dv.dv[k][a] = 0.0;
         }
-        warp_walk(t, posm, s_leaf, lane, dv, valid);
+        warp_walk<true>(t, posm, s_leaf, lane, dv, valid);
 
         if (valid) {
             const double dens_i = dv.dens;
@@ -645,7 +645,7 @@ k_fluid_force(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, con
         v.pp_i = 1.0 / (v.dens_i * v.dens_i);
     }
     v.ki.init(v.h_i);
-    warp_walk(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
+    warp_walk<false>(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
     if (valid) {
 #pragma unroll
         for (int a = 0; a < DIM; ++a) p.acc[a][i] = v.acc[a];
@@ -1066,7 +1066,7 @@ k_neighbor_lists(PSoA p, TreeDev t, DevParams P, int n, const double * __restric
         }
     }
     v.h_i2 = __dmul_rn(v.h_i, v.h_i);
-    warp_walk(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
+    warp_walk<false>(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
     if (valid && !fill) counts[i] = v.cnt;
 }
 

@@ -1,0 +1,153 @@
+"""CPU tests (-m "not gpu") of the host side: the C-ABI library loads and exports every symbol that
+include/sphb.h declares (no compute calls without a GPU), the parameter surface keeps the
+reference's keys / defaults / errors, the sample generators, and the N>1 host logic under gloo."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import parity_util as U
+from sphcode_b200 import params as P
+from sphcode_b200 import samples as S
+from sphcode_b200 import lib
+
+
+@pytest.fixture(scope="session")
+def sphb_lib():
+    lib.build()                     # nvcc cross-compiles without a GPU
+    return ctypes.CDLL(lib.LIB_PATH)
+
+
+def test_cabi_exports_every_declared_symbol(sphb_lib):
+    hdr = open(os.path.join(U.ROOT, "include", "sphb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(sphb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(sphb_lib, name), f"libsphb.so lacks {name}"
+    assert sorted(lib.SYMBOLS) == declared, "sphcode_b200/lib.py binds a different set than include/sphb.h declares"
+    for dim, size in ((1, 144), (2, 176), (3, 208)):        # sizeof(SPHParticle), include/particle.hpp:8-33
+        sphb_lib.sphb_sizeof_particle.restype = ctypes.c_size_t
+        assert sphb_lib.sphb_sizeof_particle(dim) == size == S.particle_dtype(dim).itemsize
+
+
+def test_no_cpu_fallback(sphb_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lib.SphbError, match="no CUDA device"):
+        lib.Context(P.sample_params("shock_tube"), 1)
+
+
+def test_params_struct_layout_matches_header():
+    # sphb_params in include/sphb.h: 2 ints, 3 doubles, 2 ints, 3 doubles, 2 ints, 1 double, 4 ints, 1 double,
+    # 2 ints, 6 doubles, 2 doubles, 2 ints
+    assert ctypes.sizeof(lib.SphbParams) == 8 + 24 + 8 + 24 + 8 + 8 + 16 + 8 + 8 + 48 + 16 + 8
+
+
+def test_parameter_defaults_and_errors():
+    p = P.resolve({"endTime": 1.0, "gamma": 1.4})
+    assert p["SPHType"] == "ssph" and p["cflSound"] == 0.3 and p["cflForce"] == 0.125          # src/solver.cpp:205-219
+    assert p["neighborNumber"] == 32 and p["leafParticleNumber"] == 1 and p["maxTreeLevel"] == 20
+    assert p["outputTime"] == pytest.approx(0.01) and p["energyTime"] == p["outputTime"]
+    assert p["iterativeSmoothingLength"] is True and p["theta"] == 0.5 and p["G"] == 1.0
+    with pytest.raises(P.SPHParameterError):
+        P.resolve({"gamma": 1.4})
+    with pytest.raises(P.SPHParameterError, match="Unknown SPH type"):
+        P.resolve({"endTime": 1, "gamma": 1.4, "SPHType": "xsph"})
+    with pytest.raises(P.SPHParameterError, match="kernel is unknown"):
+        P.resolve({"endTime": 1, "gamma": 1.4, "kernel": "gauss"})
+    with pytest.raises(P.SPHParameterError, match="alphaMax < alphaMin"):
+        P.resolve({"endTime": 1, "gamma": 1.4, "useTimeDependentAV": True, "alphaMax": 0.05})
+    with pytest.raises(P.SPHParameterError, match="rangeMax != DIM"):
+        P.resolve({"endTime": 1, "gamma": 1.4, "periodic": True, "rangeMax": [1.0], "rangeMin": [0.0]}, dim=2)
+    with pytest.raises(P.SPHParameterError):
+        P.sample_params("no_such_sample")
+    assert set(P.SAMPLES) == {"shock_tube", "gresho_chan_vortex", "pairing_instability", "hydrostatic", "khi", "evrard"}
+
+
+def test_sample_generators():
+    st = S.shock_tube(50, 1.4)                                   # src/sample/shock_tube.cpp:18-51
+    assert len(st) == 500 and np.isclose(st["pos"][0, 0], -0.5 + 0.00125)
+    assert np.count_nonzero(st["dens"] == 1.0) == 400 and np.count_nonzero(st["dens"] == 0.25) == 100
+    assert np.allclose(st["mass"], 0.0025)
+    k = S.khi(64, 5.0 / 3.0)                                     # src/sample/khi.cpp:18-73
+    assert len(k) == 64 * 64 * 3 // 4 and set(np.unique(k["dens"])) == {1.0, 2.0}
+    ev = S.evrard(20, 5.0 / 3.0)                                 # src/sample/evrard.cpp:19-63
+    r = np.sqrt((ev["pos"] ** 2).sum(axis=1))
+    assert len(ev) == 4224 and r.max() <= 1.0 and np.isclose(ev["mass"].sum(), 1.0)
+    assert np.allclose(ev["dens"], 1.0 / (2 * np.pi * r))
+    g = S.gresho_chan_vortex(32, 5.0 / 3.0)
+    assert len(g) == 1024 and np.isclose(g["mass"].sum(), 1.0)
+    pi1, pi2 = S.pairing_instability(16, 5.0 / 3.0), S.pairing_instability(16, 5.0 / 3.0)
+    assert np.array_equal(pi1["pos"], pi2["pos"])                # mt19937(1): deterministic
+    h = S.hydrostatic(16, 5.0 / 3.0)
+    assert set(np.unique(h["dens"])) == {1.0, 4.0}
+
+
+def _slices(n, world):
+    """Mirror of my_slice() in sphcode_b200/csrc/sphb_api.cu: rank r owns groups of 32 particles
+    [r * slice_groups, (r + 1) * slice_groups) of the sorted order."""
+    groups = -(-n // 32)
+    sg = -(-groups // world)
+    out = []
+    for r in range(world):
+        f = min(r * sg * 32, n)
+        l = min(n, r * sg * 32 + sg * 32)
+        out.append((f, max(0, l - f)))
+    return out, sg * world * 32
+
+
+@pytest.mark.parametrize("n,world", [(500, 2), (998592, 8), (33, 4), (15902832, 8), (31, 2)])
+def test_slices_tile_the_particle_range(n, world):
+    sl, n_pad = _slices(n, world)
+    assert sum(c for _, c in sl) == n and n_pad >= n and n_pad % (32 * world) == 0
+    pos = 0
+    for f, c in sl:
+        assert f == pos or c == 0
+        assert c == 0 or f % 32 == 0
+        pos += c
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the unique-id hand-off of bench.py: rank 0 creates 128 bytes, everyone receives the same bytes
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid.copy_(torch.arange(128, dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    # replicated state, sliced compute, all-gather of the slice results (what gather_d() does with NCCL)
+    n = 1000
+    sl, n_pad = _slices(n, world)
+    mine = torch.zeros(n_pad // world, dtype=torch.float64)
+    f, c = sl[rank]
+    mine[:c] = torch.arange(f, f + c, dtype=torch.float64) * 2.0
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    whole = torch.cat(parts)[:n]
+    # dt: min over the ranks' slice minima (all-reduce min)
+    dtm = torch.tensor([float(rank + 1)], dtype=torch.float64)
+    dist.all_reduce(dtm, op=dist.ReduceOp.MIN)
+    q.put((rank, bytes(uid.numpy().tobytes()), bool(torch.equal(whole, torch.arange(n, dtype=torch.float64) * 2.0)), float(dtm)))
+    dist.destroy_process_group()
+
+
+def test_multi_rank_host_logic_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 29731
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p_ in procs:
+        p_.join(timeout=60)
+    assert all(r[1] == bytes(range(128)) for r in res)
+    assert all(r[2] for r in res) and all(r[3] == 1.0 for r in res)
