@@ -41,6 +41,11 @@
 #include "gsph/g_fluid_force.hpp"
 #include "exhaustive_search.hpp"
 #include "kernel/kernel_function.hpp"
+#ifdef SPHB_GPU_MODULES
+// Same driver, but the module slots are filled with the sph::gpu drop-ins
+// (sphcode_b200/host/gpu_modules.hpp): the integration test of the plugin boundary.
+#include "gpu_modules.hpp"
+#endif
 
 // ---- Logger statics (stand-in for src/logger.cpp, which needs boost::format) ----
 namespace sph {
@@ -152,6 +157,18 @@ ref_ctx * ref_create(const ref_params * p, int n, const void * particles)
         c->sim->set_particle_num(n);
 
         // module selection: src/solver.cpp:359-370
+#ifdef SPHB_GPU_MODULES
+        c->timestep = std::make_shared<gpu::TimeStep>();
+        if(c->param->type == SPHType::SSPH) {
+            c->pre = std::make_shared<gpu::PreInteraction>();
+            c->fforce = std::make_shared<gpu::FluidForce>();
+        } else if(c->param->type == SPHType::DISPH) {
+            c->pre = std::make_shared<gpu::disph::PreInteraction>();
+            c->fforce = std::make_shared<gpu::disph::FluidForce>();
+        } else {
+            c->pre = std::make_shared<gpu::gsph::PreInteraction>();
+            c->fforce = std::make_shared<gpu::gsph::FluidForce>();
+#else
         c->timestep = std::make_shared<TimeStep>();
         if(c->param->type == SPHType::SSPH) {
             c->pre = std::make_shared<PreInteraction>();
@@ -162,6 +179,7 @@ ref_ctx * ref_create(const ref_params * p, int n, const void * particles)
         } else {
             c->pre = std::make_shared<gsph::PreInteraction>();
             c->fforce = std::make_shared<gsph::FluidForce>();
+#endif
             // src/solver.cpp:373-385
             std::vector<std::string> names = {"grad_density", "grad_pressure", "grad_velocity_0"};
 #if DIM >= 2
@@ -172,7 +190,11 @@ ref_ctx * ref_create(const ref_params * p, int n, const void * particles)
 #endif
             c->sim->add_vector_array(names);
         }
+#ifdef SPHB_GPU_MODULES
+        c->gforce = std::make_shared<gpu::GravityForce>();
+#else
         c->gforce = std::make_shared<GravityForce>();
+#endif
         c->timestep->initialize(c->param);
         c->pre->initialize(c->param);
         c->fforce->initialize(c->param);
@@ -183,7 +205,13 @@ ref_ctx * ref_create(const ref_params * p, int n, const void * particles)
     return c;
 }
 
-void ref_destroy(ref_ctx * c) { delete c; }
+void ref_destroy(ref_ctx * c)
+{
+#ifdef SPHB_GPU_MODULES
+    if(c && c->sim) gpu::release(c->sim.get());
+#endif
+    delete c;
+}
 const char * ref_error(ref_ctx * c) { return c->err.c_str(); }
 
 void ref_get_particles(ref_ctx * c, void * out)

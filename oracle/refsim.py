@@ -89,6 +89,10 @@ def build(target="all", verbose=False):
 def lib_path(dim, flavour):
     if flavour == "port":
         return os.path.join(_HERE, "libspho.so")
+    if flavour == "gpumod":
+        # the reference driver with the sph::gpu Module drop-ins in the module slots
+        # (sphcode_b200/host/Makefile): integration test of the plugin boundary, needs a GPU
+        return os.path.join(_HERE, "..", "sphcode_b200", "host", "_build", f"libsphgpu_d{dim}.so")
     suffix = {"tree": "", "exhaustive": "_ex"}[flavour]
     return os.path.join(_HERE, "_ref", f"libsphref_d{dim}{suffix}.so")
 

@@ -197,3 +197,30 @@ def test_counters_and_error_paths():
     bad = dict(p, kernel="wendland")
     with pytest.raises(SphbError):
         Context(bad, 1)
+
+
+@pytest.mark.parametrize("name", ["shock_tube_c1", "khi_disph_ac", "gresho_gsph2", "evrard_c4", "evrard_ssph_cubic"])
+def test_module_dropin_matches_reference(name):
+    """The plugin boundary itself: oracle/ref_driver.cpp built with -DSPHB_GPU_MODULES fills the
+    reference Solver's four module slots (src/solver.cpp:359-370) with the sph::gpu classes of
+    sphcode_b200/host/gpu_modules.cpp; everything else (Simulation, host predict / correct, the call
+    order of Solver::initialize / integrate) is the reference's.  Compared with the same driver
+    running the reference's own modules."""
+    p, parts = U.make_case(name)
+    dim = p["DIM"]
+    from oracle import refsim
+    if not (refsim.available(dim, "gpumod") and refsim.available(dim, "tree")):
+        pytest.skip("host module library / oracle/_ref not built on this box (needs /root/reference at build time)")
+    ref = refsim.RefSim(p, parts, dim, "tree")
+    gpu = refsim.RefSim(p, parts, dim, "gpumod")
+    ref.initialize(); gpu.initialize()
+    U.assert_fields(gpu.particles, ref.particles, U.PRE_FIELDS + U.FORCE_FIELDS, what=f"{name} modules initialize", params=p)
+    for s in range(2):
+        a, b = ref.integrate(), gpu.integrate()
+        assert abs(a - b) <= RTOL * a
+        U.assert_fields(gpu.particles, ref.particles, U.STEP_FIELDS, what=f"{name} modules step {s + 1}", params=p)
+    if p["SPHType"] == "gsph":
+        g, r = gpu.vector_array("grad_pressure"), ref.vector_array("grad_pressure")
+        s0 = ref.particles
+        assert np.abs(g - r).max() <= RTOL * (np.abs(r).max() + (s0["pres"] / s0["sml"]).max())
+    gpu.close()
