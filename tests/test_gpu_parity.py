@@ -224,3 +224,17 @@ def test_module_dropin_matches_reference(name):
         s0 = ref.particles
         assert np.abs(g - r).max() <= RTOL * (np.abs(r).max() + (s0["pres"] / s0["sml"]).max())
     gpu.close()
+
+
+def test_two_gpu_slices_match_golden():
+    """N>1 path on real GPUs (skipped on a 1-GPU box): tests/dist_check.py under torchrun, 2 ranks."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29741",
+                        __import__("os").path.join(U.ROOT, "tests", "dist_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
