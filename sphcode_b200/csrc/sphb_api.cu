@@ -84,14 +84,20 @@ struct sphb_ctx {
     double * d_root = nullptr;             // centre[3], edge
     double * d_bbox_part = nullptr; int bbox_blocks = 0;
     double * d_scal = nullptr;             // [0] dt, [1] h_per_v_sig, [2] dt_force_min, [3..5] energy
-    unsigned long long * d_err = nullptr;  // [0] newton non-converged, [1] list overflow
+    unsigned long long * d_err = nullptr;  // [0] newton non-converged, [1] list overflow, [2] walk error bits
     Counters * d_cnt = nullptr;
     int * d_group_counter = nullptr;
     double dt = 0.0, hpvs = 0.0;
     bool first_pre = true;
     unsigned long long nonconverged_total = 0;
 
-    double * scratch_r = nullptr, * scratch_m = nullptr; int pre_grid = 0;
+    double * scratch_r = nullptr, * scratch_m = nullptr; int * scratch_j = nullptr; int pre_grid = 0;
+    unsigned char * grp_flags = nullptr;   // 1 where a group starts (tree order)
+    int * grp_start = nullptr;             // first particle of every group, ascending
+    int * d_ngroups = nullptr;             // number of groups (device)
+    int * d_grp_ctl = nullptr;             // [0] work counter, [1] end group of the current kernel
+    Recs rc{};                             // packed gather records (tree order)
+    bool recs_dirty = true;                // SoA fields changed since the records were packed
 
     void * d_aos = nullptr; size_t d_aos_bytes = 0;
     void * h_stage = nullptr; size_t h_stage_bytes = 0;
@@ -196,17 +202,26 @@ int alloc_particles(sphb_ctx * c, int n)
     cub::DeviceRadixSort::SortPairs(nullptr, c->cub_tmp_bytes, c->keys, c->keys_alt, c->idx, c->idx_alt, n, 0, 64, c->stream);
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int *)nullptr, (int *)nullptr, 5 * n + 2, c->stream);
-    c->cub_tmp_bytes = std::max(c->cub_tmp_bytes, scan_bytes) + 256;
+    size_t sel_bytes = 0;
+    cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), (unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, n, c->stream);
+    c->cub_tmp_bytes = std::max(std::max(c->cub_tmp_bytes, scan_bytes), sel_bytes) + 256;
     { char * t = nullptr; if (dev_alloc(c, &t, c->cub_tmp_bytes, c->allocs)) return 1; c->cub_tmp = t; }
     c->bbox_blocks = std::min(cdiv(n, 256), 4 * c->sm_count);
     if (dev_alloc(c, &c->d_bbox_part, (size_t)c->bbox_blocks * 6, c->allocs)) return 1;
 
-    // Newton scratch: one r (and m) column set per resident warp of the persistent pre kernel
+    // list scratch: one r, j (and m) column set per resident warp of the persistent pre / force kernels
     c->pre_grid = std::min(cdiv(groups, 4), c->sm_count * 4);
     const size_t slots = (size_t)c->pre_grid * 4;
     if (dev_alloc(c, &c->scratch_r, slots * c->P.list_cap * 32, c->allocs)) return 1;
+    if (dev_alloc(c, &c->scratch_j, slots * c->P.list_cap * 32, c->allocs)) return 1;
     if (c->P.sph_type != T_DISPH) { if (dev_alloc(c, &c->scratch_m, slots * c->P.list_cap * 32, c->allocs)) return 1; }
     else c->scratch_m = nullptr;
+    if (dev_alloc(c, &c->grp_flags, np + 32, c->allocs) || dev_alloc(c, &c->grp_start, np + 32, c->allocs)) return 1;
+    // packed gather records
+    if (dev_alloc(c, &c->rc.posm, np, c->allocs) || dev_alloc(c, &c->rc.velc, np, c->allocs) ||
+        dev_alloc(c, &c->rc.thermo, np, c->allocs) || dev_alloc(c, &c->rc.av, np, c->allocs) ||
+        dev_alloc(c, &c->rc.hsoft, np, c->allocs)) return 1;
+    c->recs_dirty = true;
 
     c->d_aos_bytes = (size_t)n * rec_size(c->dim);
     { char * t = nullptr; if (dev_alloc(c, &t, c->d_aos_bytes, c->allocs)) return 1; c->d_aos = t; }
@@ -225,9 +240,9 @@ int alloc_nodes(sphb_ctx * c, int cap, int keep, int keep_offs = 0)
     old_bag.swap(c->node_allocs);
     TreeBuild & t = c->tb;
     t = TreeBuild{};
-    int ** ia[] = {&t.first, &t.count, &t.level, &t.parent, &t.child0, &t.nchild, &t.size, &t.dfs};
-    int * const oi[] = {old.first, old.count, old.level, old.parent, old.child0, old.nchild, old.size, old.dfs};
-    for (int k = 0; k < 8; ++k) {
+    int ** ia[] = {&t.first, &t.count, &t.level, &t.parent, &t.child0, &t.nchild};
+    int * const oi[] = {old.first, old.count, old.level, old.parent, old.child0, old.nchild};
+    for (int k = 0; k < 6; ++k) {
         if (dev_alloc(c, ia[k], cap, c->node_allocs)) return 1;
         if (keep) CK(cudaMemcpyAsync(*ia[k], oi[k], (size_t)keep * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -317,10 +332,28 @@ __global__ void k_set_scalars(double * s, double dt, double hpvs, int which)
     if (which & 2) s[1] = hpvs;
 }
 
-// gather records in memory that is dead between make_tree calls (the inactive SoA side):
-// {x,y,z,m} per particle in its first four arrays, {2/h, h^2} in the next two
-double4 * posm_of(sphb_ctx * c) { return reinterpret_cast<double4 *>(c->alt.pos[0]); }
-double2 * hsoft_of(sphb_ctx * c) { return reinterpret_cast<double2 *>(c->alt.pos[0] + (size_t)4 * c->n_pad); }
+// (re)pack the gather records from the SoA state: what = 1 posm | 2 velc | 4 thermo + av
+int pack_recs(sphb_ctx * c, int what)
+{
+    const int n = c->n, B = 256;
+    switch (c->dim) {
+    case 1: k_pack_recs<1><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what); break;
+    case 2: k_pack_recs<2><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what); break;
+    default: k_pack_recs<3><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what); break;
+    }
+    LAUNCH_CHECK();
+    if (what == 7) c->recs_dirty = false;
+    return 0;
+}
+int ensure_recs(sphb_ctx * c) { return c->recs_dirty ? pack_recs(c, 7) : 0; }
+
+// group table view for a kernel that works on the particles [p_begin, p_end) (group boundaries)
+int group_table(sphb_ctx * c, int p_begin, int p_end, GroupTable & gt)
+{
+    k_group_range<<<1, 32, 0, c->stream>>>(c->grp_start, c->d_ngroups, p_begin, p_end, c->d_grp_ctl); LAUNCH_CHECK();
+    gt.start = c->grp_start; gt.n_groups = c->d_ngroups; gt.ctl = c->d_grp_ctl; gt.n = c->n;
+    return 0;
+}
 
 // ---- tree ---------------------------------------------------------------------------------------------
 template <int DIM> int make_tree_t(sphb_ctx * c)
@@ -377,13 +410,17 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         const int a = c->levels[l].first, b = c->levels[l].second;
         k_level_up<DIM><<<cdiv(b - a, B), B, 0, c->stream>>>(c->tb, c->cur, a, b); LAUNCH_CHECK();
     }
-    for (size_t l = 0; l < c->levels.size(); ++l) {
-        const int a = c->levels[l].first, b = c->levels[l].second;
-        k_level_dfs<<<cdiv(b - a, B), B, 0, c->stream>>>(c->tb, a, b); LAUNCH_CHECK();
-    }
     c->td.n_nodes = n_nodes;
     k_tree_scatter<DIM><<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, c->td, n_nodes, c->d_root); LAUNCH_CHECK();
-    k_pack_posm<DIM><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, posm_of(c), n); LAUNCH_CHECK();
+    if (pack_recs(c, 7)) return 1;
+    // particle groups (sphb_tree.cuh): flags at group starts -> ascending list of starts
+    CK(cudaMemsetAsync(c->grp_flags, 0, (size_t)n, c->stream));
+    k_group_flags<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->world > 1 ? c->slice_groups * 32 : 0, n); LAUNCH_CHECK();
+    {
+        size_t tb = c->cub_tmp_bytes;
+        CK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, cub::CountingInputIterator<int>(0), c->grp_flags, c->grp_start, c->d_ngroups, n, c->stream));
+        ++c->launches;
+    }
     c->tree_valid = true;
     c->last_counters.tree_nodes = (uint64_t)n_nodes;
     return 0;
@@ -429,21 +466,21 @@ template <int DIM, int KT, int SPH> int pre_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_PRE);
     const Slice s = my_slice(c);
-    const int g0 = s.first_particle / 32;
-    const int ng = cdiv(s.n_local, 32);
+    GroupTable gt;
     if (c->first_pre) {
         // initial_smoothing needs every particle's density before the main pass: all ranks do all
         // particles (first call only)
-        k_initial_smoothing<DIM, KT><<<cdiv(cdiv(c->n, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n, posm_of(c)); LAUNCH_CHECK();
+        if (ensure_recs(c) || group_table(c, 0, c->n, gt)) return 1;
+        k_initial_smoothing<DIM, KT><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt, c->d_err); LAUNCH_CHECK();
         c->first_pre = false;
+        c->recs_dirty = true;             // dens changed
     }
+    if (ensure_recs(c)) return 1;
     k_set_scalars<<<1, 1, 0, c->stream>>>(c->d_scal, 0.0, DBL_MAX, 2); LAUNCH_CHECK();
-    // group counter starts at g0; the kernel stops at g0 + ng
-    CK(cudaMemcpyAsync(c->d_group_counter, &g0, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    if (ng > 0) {
-        const int grid = std::min(c->pre_grid, cdiv(ng, 4));
-        k_pre_interaction<DIM, KT, SPH><<<grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n, g0 + ng, c->d_group_counter,
-            c->scratch_r, c->scratch_m, c->d_scal + 0, c->d_scal + 1, c->d_err, c->counters_on ? c->d_cnt : nullptr, posm_of(c));
+    if (s.n_local > 0) {
+        if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
+        k_pre_interaction<DIM, KT, SPH><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt,
+            c->scratch_r, c->scratch_m, c->scratch_j, c->d_scal + 0, c->d_scal + 1, c->d_err, c->counters_on ? c->d_cnt : nullptr);
         LAUNCH_CHECK();
     }
     if (c->world > 1) {
@@ -459,6 +496,7 @@ template <int DIM, int KT, int SPH> int pre_t(sphb_ctx * c)
         }
         CKN(g_nccl.AllReduce(c->d_scal + 1, c->d_scal + 1, 1, ncclFloat64, ncclMin, c->comm, c->stream));
         CKN(g_nccl.GroupEnd());
+        if (pack_recs(c, 4)) return 1;    // the other ranks' h, dens, pres, gradh, alpha, balsara
     }
     return set_kernel(c);
 }
@@ -482,9 +520,12 @@ template <int DIM, int KT, int SPH> int force_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_FLUID);
     const Slice s = my_slice(c);
+    if (ensure_recs(c)) return 1;
     if (s.n_local > 0) {
-        k_fluid_force<DIM, KT, SPH><<<cdiv(cdiv(s.n_local, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n,
-            s.first_particle, s.first_particle + s.n_local, c->d_scal + 0, c->counters_on ? c->d_cnt : nullptr, posm_of(c));
+        GroupTable gt;
+        if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
+        k_fluid_force<DIM, KT, SPH><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt,
+            c->scratch_j, c->d_scal + 0, c->d_err, c->counters_on ? c->d_cnt : nullptr);
         LAUNCH_CHECK();
     }
     return 0;
@@ -514,9 +555,11 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
         return 0;
     }
     if (s.n_local > 0) {
-        k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, hsoft_of(c), c->n); LAUNCH_CHECK();
-        k_gravity<DIM><<<cdiv(cdiv(s.n_local, 32), 4), 128, 0, c->stream>>>(c->cur, c->td, c->P, c->n,
-            s.first_particle, s.first_particle + s.n_local, posm_of(c), hsoft_of(c), c->counters_on ? c->d_cnt : nullptr);
+        if (ensure_recs(c)) return 1;
+        k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, c->rc.hsoft, c->n); LAUNCH_CHECK();
+        GroupTable gt;
+        if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
+        k_gravity<DIM><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, c->counters_on ? c->d_cnt : nullptr, c->d_err);
         LAUNCH_CHECK();
     }
     return 0;
@@ -558,12 +601,14 @@ template <int DIM> int predict_t(sphb_ctx * c)
     Timer tm(c, SPHB_T_PREDICT);
     k_predict<DIM><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n, c->d_scal + 0); LAUNCH_CHECK();
     c->tree_valid = false;
+    c->recs_dirty = true;
     return 0;
 }
 template <int DIM> int correct_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_CORRECT);
     k_correct<DIM><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n, c->d_scal + 0); LAUNCH_CHECK();
+    c->recs_dirty = true;
     return 0;
 }
 
@@ -581,7 +626,7 @@ int correct(sphb_ctx * c) { return DIM_SWITCH(c, correct_t<1>(c), correct_t<2>(c
 // copy dt, h_per_v_sig and the error counters to the host; turn device-side errors into a status
 int sync_scalars(sphb_ctx * c)
 {
-    double s[2]; unsigned long long e[2];
+    double s[2]; unsigned long long e[3];
     CK(cudaMemcpyAsync(s, c->d_scal, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(e, c->d_err, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -590,6 +635,11 @@ int sync_scalars(sphb_ctx * c)
     if (e[1]) {
         c->err = "neighbor list overflow: a particle has more than neighborNumber*20 candidates (include/defines.hpp:29)";
         CK(cudaMemsetAsync(c->d_err + 1, 0, sizeof(unsigned long long), c->stream));
+        return 1;
+    }
+    if (e[2]) {
+        c->err = (e[2] & WALK_ERR_GRAV_STACK) ? "gravity walk: node stack overflow" : "neighbour walk: node stack overflow";
+        CK(cudaMemsetAsync(c->d_err + 2, 0, sizeof(unsigned long long), c->stream));
         return 1;
     }
     if (c->timers_on) {
@@ -650,11 +700,13 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
     void * q = nullptr;
     cudaMalloc(&q, 4 * sizeof(double)); c->d_root = (double *)q;
     cudaMalloc(&q, 8 * sizeof(double)); c->d_scal = (double *)q;
-    cudaMalloc(&q, 2 * sizeof(unsigned long long)); c->d_err = (unsigned long long *)q;
+    cudaMalloc(&q, 4 * sizeof(unsigned long long)); c->d_err = (unsigned long long *)q;
     cudaMalloc(&q, sizeof(Counters)); c->d_cnt = (Counters *)q;
     cudaMalloc(&q, sizeof(int)); c->d_group_counter = (int *)q;
+    cudaMalloc(&q, sizeof(int)); c->d_ngroups = (int *)q;
+    cudaMalloc(&q, 2 * sizeof(int)); c->d_grp_ctl = (int *)q;
     cudaMemset(c->d_scal, 0, 8 * sizeof(double));
-    cudaMemset(c->d_err, 0, 2 * sizeof(unsigned long long));
+    cudaMemset(c->d_err, 0, 4 * sizeof(unsigned long long));
     cudaMemset(c->d_cnt, 0, sizeof(Counters));
     if (P.periodic) {
         // BHTree::initialize, src/bhtree.cpp:19-31
@@ -681,7 +733,7 @@ void sphb_destroy(sphb_ctx * c)
     cudaStreamSynchronize(c->stream);
     if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     free_bag(c->allocs); free_bag(c->node_allocs);
-    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter);
+    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter); cudaFree(c->d_ngroups); cudaFree(c->d_grp_ctl);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->own_stream);
@@ -759,6 +811,7 @@ int sphb_upload_aos(sphb_ctx * c, const void * particles, int n, size_t stride, 
     default: k_unpack<3><<<cdiv(n, 256), 256, 0, c->stream>>>((const char *)c->d_aos, rec, c->cur, n, mask, first); break;
     }
     LAUNCH_CHECK();
+    c->recs_dirty = true;
     if (mask & (SPHB_F_POS | SPHB_F_MASS)) c->tree_valid = false;
     CK(cudaStreamSynchronize(c->stream));        // the caller may reuse its buffer
     return 0;
@@ -862,6 +915,7 @@ int sphb_init_state(sphb_ctx * c)
     CK(cudaSetDevice(c->device));
     if (!c->n) { c->err = "no particles uploaded"; return 1; }
     k_init_state<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n); LAUNCH_CHECK();
+    c->recs_dirty = true;
     return 0;
 }
 
@@ -964,6 +1018,7 @@ int sphb_neighbor_lists(sphb_ctx * c, const double * h, int symmetric, int64_t *
     CK(cudaSetDevice(c->device));
     if (require_tree(c)) return 1;
     const int n = c->n;
+    if (ensure_recs(c)) return 1;
     if (symmetric) { if (set_kernel(c)) return 1; }
     std::vector<void *> bag;
     double * d_h = nullptr; int * d_counts = nullptr; long long * d_offs = nullptr; int * d_ids = nullptr;
@@ -974,8 +1029,8 @@ int sphb_neighbor_lists(sphb_ctx * c, const double * h, int symmetric, int64_t *
         k_gather_by_orig<<<cdiv(n, 256), 256, 0, c->stream>>>(d_h_orig, c->cur.orig, d_h, n, 1, 0); LAUNCH_CHECK();
     }
     if (dev_alloc(c, &d_counts, n, bag) || dev_alloc(c, &d_offs, n + 1, bag)) { free_bag(bag); return 1; }
-    const int grid = cdiv(cdiv(n, 32), 4);
-#define NL(D, FILL) k_neighbor_lists<D><<<grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, n, d_h, symmetric, FILL, d_counts, d_offs, d_ids, cap_total, posm_of(c))
+    GroupTable gt;
+#define NL(D, FILL) if (group_table(c, 0, n, gt)) { free_bag(bag); return 1; } k_neighbor_lists<D><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt, d_h, symmetric, FILL, d_counts, d_offs, d_ids, cap_total, c->d_err)
     switch (c->dim) { case 1: NL(1, 0); break; case 2: NL(2, 0); break; default: NL(3, 0); break; }
     LAUNCH_CHECK();
     std::vector<int> counts(n), orig(n);
@@ -1036,8 +1091,8 @@ int sphb_get_counters(sphb_ctx * c, sphb_counters * out)
         CK(cudaMemcpy(nn.data(), c->td.nn, nn.size() * sizeof(double2), cudaMemcpyDeviceToHost));
         uint64_t leaves = 0;
         for (int k = 0; k < c->td.n_nodes; ++k) {
-            long long bits; std::memcpy(&bits, &nn[(size_t)k * 4 + 3].x, 8);
-            leaves += (bits >> 32) ? 1 : 0;
+            long long bits; std::memcpy(&bits, &nn[(size_t)k * 4 + 2].y, 8);
+            leaves += (bits >> 32) ? 0 : 1;          // {child0, nchild}: nchild == 0
         }
         o.tree_leaves = leaves; o.tree_nodes = (uint64_t)c->td.n_nodes;
     }

@@ -12,7 +12,7 @@
 // per-lane list is the r (and m) column of the Newton iteration, which must see one fixed
 // candidate set several times (src/pre_interaction.cpp:227-283).
 #pragma once
-#include "sphb_tree.cuh"
+#include "sphb_walk.cuh"
 
 namespace sphb {
 
@@ -43,6 +43,36 @@ template <int DIM> __device__ __forceinline__ double h_guess(int ngb, double mas
     return cbrt(x);
 }
 
+// Packed gather records (tree order), 32 bytes each, so that a pair body fetches a neighbour with a few
+// 16-byte loads instead of one scattered 8-byte load per field:
+//   posm   {x, y, z, m}            rebuilt by make_tree
+//   velc   {vx, vy, vz, c}         c = sound speed
+//   thermo {u, h, dens, pres}      u before PreInteraction; h, dens, pres written by PreInteraction
+//   av     {gradh, alpha, balsara, -}   written by PreInteraction
+//   hsoft  {2/h, h^2}              gravity softening record
+struct Recs { double4 *posm, *velc, *thermo, *av; double2 *hsoft; };
+
+template <int DIM>
+__global__ void k_pack_recs(PSoA p, Recs r, int n, int what)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int Y = DIM >= 2 ? 1 : 0, Z = DIM >= 3 ? 2 : 0;
+    if (what & 1) r.posm[i] = make_double4(p.pos[0][i], DIM >= 2 ? p.pos[Y][i] : 0.0, DIM >= 3 ? p.pos[Z][i] : 0.0, p.mass[i]);
+    if (what & 2) r.velc[i] = make_double4(p.vel[0][i], DIM >= 2 ? p.vel[Y][i] : 0.0, DIM >= 3 ? p.vel[Z][i] : 0.0, p.sound[i]);
+    if (what & 4) {
+        r.thermo[i] = make_double4(p.ene[i], p.sml[i], p.dens[i], p.pres[i]);
+        r.av[i] = make_double4(p.gradh[i], p.alpha[i], p.balsara[i], 0.0);
+    }
+}
+
+template <int DIM> __device__ __forceinline__ void vec_from4(const double4 & q, double (&o)[DIM])
+{
+    o[0] = q.x;
+    if (DIM >= 2) o[DIM >= 2 ? 1 : 0] = q.y;
+    if (DIM >= 3) o[DIM >= 3 ? 2 : 0] = q.z;
+}
+
 // =================================================================================================
 // initial_smoothing, src/pre_interaction.cpp:171-215: dens_i = sum_{r < h} m_j W(r, h), h = guess
 // =================================================================================================
@@ -51,30 +81,27 @@ struct InitSmoothV {
     const DevParams & P;
     double ri[DIM], h, h2, dens;
     KernelCoef<DIM, KT> kc;
-    __device__ __forceinline__ bool open(const NodeRec & nd) { return node_in_reach<DIM>(P, nd, ri, h); }
-    __device__ __forceinline__ void leaf(const NodeRec &, int, int m, const double4 * sl)
+    __device__ __forceinline__ void hit(int, const double4 & pj, double)
     {
-#pragma unroll 4
-        for (int k = 0; k < m; ++k) {
-            const double4 pj = sl[k];
-            double d[DIM];
-            rij_from4<DIM>(P, ri, pj, d);
-            const double r2 = abs2_exact<DIM>(d);
-            if (r2 < h2) {
-                const double r = sqrt(r2);
-                if (r < h) dens += pj.w * kc.w(r);
-            }
+        double d[DIM];
+        rij_from4<DIM>(P, ri, pj, d);
+        const double r2 = abs2_exact<DIM>(d);
+        if (r2 < h2) {
+            const double r = sqrt(r2);
+            if (r < h) dens += pj.w * kc.w(r);
         }
     }
 };
 
 template <int DIM, int KT>
-__global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, TreeDev t, DevParams P, int n, const double4 * __restrict__ posm)
+__global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt, unsigned long long * __restrict__ d_err)
 {
-    __shared__ double4 s_leaf[4][32];
+    __shared__ NWalkSmem s_walk[4];
     const int lane = threadIdx.x & 31;
-    const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
-    const bool valid = i < n;
+    int g_first, g_cnt;
+    while (next_group(gt, lane, g_first, g_cnt)) {
+    const int i = g_first + lane;
+    const bool valid = lane < g_cnt;
     InitSmoothV<DIM, KT> v{P};
     v.dens = 0.0;
     v.h = 1.0;
@@ -87,54 +114,46 @@ __global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, TreeDev t, De
     }
     v.h2 = __dmul_rn(v.h, v.h);
     v.kc.init(v.h);
-    warp_walk<true>(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
+    group_stream<DIM, false>(t, P, rc.posm, nullptr, 0, s_walk[threadIdx.x >> 5], lane, v.ri, v.h, valid, v, d_err);
     if (valid) { p.sml[i] = v.h; p.dens[i] = v.dens; }
+    }
 }
 
 // =================================================================================================
 // PreInteraction::calculation
 // =================================================================================================
-// walk 1: candidate set {j : r2 < h_search^2} (src/bhtree.cpp:251-261) -> per-lane r (and m) column
+// candidate set {j : r2 < h_search^2} (src/bhtree.cpp:251-261) -> per-lane columns r, j (and m) in
+// the warp's scratch slot (column layout [k][lane]: every later pass reads them coalesced)
 template <int DIM, bool NEED_M>
 struct CollectV {
     const DevParams & P;
-    double ri[DIM], hs, hs2;
-    double * lr; double * lm;
+    double ri[DIM], hs2;
+    double * lr; double * lm; int * lj;
     int cap, cnt, lane;
-    __device__ __forceinline__ bool open(const NodeRec & nd) { return node_in_reach<DIM>(P, nd, ri, hs); }
-    __device__ __forceinline__ void leaf(const NodeRec &, int, int m, const double4 * sl)
+    __device__ __forceinline__ void hit(int j, const double4 & pj, double)
     {
-#pragma unroll 4
-        for (int k = 0; k < m; ++k) {
-            const double4 pj = sl[k];
-            double d[DIM];
-            rij_from4<DIM>(P, ri, pj, d);
-            const double r2 = abs2_exact<DIM>(d);
-            if (r2 < hs2) {
-                if (cnt < cap) {
-                    lr[cnt * 32 + lane] = sqrt(r2);
-                    if (NEED_M) lm[cnt * 32 + lane] = pj.w;
-                }
-                ++cnt;
+        double d[DIM];
+        rij_from4<DIM>(P, ri, pj, d);
+        const double r2 = abs2_exact<DIM>(d);
+        if (r2 < hs2) {
+            if (cnt < cap) {
+                lr[cnt * 32 + lane] = sqrt(r2);
+                lj[cnt * 32 + lane] = j;
+                if (NEED_M) lm[cnt * 32 + lane] = pj.w;
             }
+            ++cnt;
         }
     }
 };
 
-// Leaf handlers of the heavy passes work in two stages so that the expensive pair body is not
-// executed under the (very sparse) per-particle hit predicate: stage 1 streams the leaf's particles
-// with warp-uniform loads and records a per-lane hit mask (cheap, convergent); stage 2 lets every
-// lane walk its own mask, so lanes with hits at DIFFERENT j run the pair body together (their loads
-// fall into the same one or two cache lines of the leaf's contiguous range).
-
-// walk 2: sums over {j : r2 < h_search^2 and r < h_i}: density pass + Balsara / MUSCL-gradient pass
+// sums over {j : r2 < h_search^2 and r < h_i}: density pass + Balsara / MUSCL-gradient pass
 // (the reference runs them as two loops over the same sorted list prefix,
 //  src/pre_interaction.cpp:83-103 and 116-161; the second only needs dens_i at the very end)
 template <int DIM, int KT, int SPH>
-struct DensityV {
-    const DevParams & P; const PSoA & p;
+struct DensityAcc {
+    const DevParams & P; const PSoA & p; const Recs & rc;
     int i;
-    double ri[DIM], vi[DIM], hs2, h, reach, hit2, ci, ui;   // hit2: cheap stage-1 bound >= min(hs2, h^2)
+    double ri[DIM], vi[DIM], ci, ui;
     KernelCoef<DIM, KT> kc;
     bool need_div;
     // accumulators
@@ -143,112 +162,93 @@ struct DensityV {
     double div_v, rot_v[3];
     double dd[DIM], du[DIM], dv[DIM][DIM];   // GSPH
 
-    __device__ __forceinline__ bool open(const NodeRec & nd) { return node_in_reach<DIM>(P, nd, ri, reach); }
-    __device__ __forceinline__ void leaf(const NodeRec &, int base, int m, const double4 * sl)
+    __device__ __forceinline__ void pair(int j, double r)
     {
-        unsigned hits = 0;
-#pragma unroll 4
-        for (int k = 0; k < m; ++k) {
-            double d[DIM];
-            rij_from4<DIM>(P, ri, sl[k], d);
-            const double r2 = abs2_exact<DIM>(d);
-            if (r2 < hit2) hits |= 1u << k;
+        const double4 pj = ldg4(&rc.posm[j]);
+        const double4 vc = ldg4(&rc.velc[j]);
+        double d[DIM];
+        rij_from4<DIM>(P, ri, pj, d);
+        ++n_neighbor;
+        const double mj = pj.w;
+        const double w = kc.w(r);
+        dens += mj * w;
+        double uj = 0.0;
+        if (SPH == T_SSPH) {
+            dh_dens += mj * kc.dhw(r);
+        } else if (SPH == T_DISPH) {
+            const double dhw = kc.dhw(r);
+            uj = __ldg(&rc.thermo[j].x);
+            n_i += w;
+            pres += mj * uj * w;
+            dh_pres += mj * uj * dhw;
+            dh_n += dhw;
         }
-        while (hits) {
-            const int kb = __ffs(hits) - 1;
-            const int j = base + kb;
-            hits &= hits - 1;
-            const double4 pj = sl[kb];
-            double d[DIM];
-            rij_from4<DIM>(P, ri, pj, d);
-            const double r2 = abs2_exact<DIM>(d);
-            if (!(r2 < hs2)) continue;
-            const double r = sqrt(r2);
-            if (r >= h) continue;                       // the `break` of the sorted loop
-            ++n_neighbor;
-            const double mj = pj.w;
-            const double w = kc.w(r);
-            dens += mj * w;
-            double uj = 0.0;
-            if (SPH == T_SSPH) {
-                dh_dens += mj * kc.dhw(r);
-            } else if (SPH == T_DISPH) {
-                const double dhw = kc.dhw(r);
-                uj = p.ene[j];
-                n_i += w;
-                pres += mj * uj * w;
-                dh_pres += mj * uj * dhw;
-                dh_n += dhw;
-            }
-            double vij[DIM];
-            {
-                double vj[DIM];
-                load_vec<DIM>(p.vel, j, vj);
+        double vij[DIM];
+        {
+            double vj[DIM];
+            vec_from4<DIM>(vc, vj);
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) vij[k] = vi[k] - vj[k];
-            }
-            if (j != i) {
-                const double v_sig = ci + p.sound[j] - 3.0 * dot<DIM>(d, vij) / r;
-                if (v_sig > v_sig_max) v_sig_max = v_sig;
-            }
-            if (SPH == T_GSPH) {
-                if (P.gsph2) {
-                    const double c = kc.dwc(r);
-                    const double uji = p.ene[j] - ui;
-#pragma unroll
-                    for (int a = 0; a < DIM; ++a) {
-                        const double dwa = d[a] * c;
-                        dd[a] += dwa * mj;
-                        du[a] += dwa * (mj * uji);
-#pragma unroll
-                        for (int k = 0; k < DIM; ++k) dv[k][a] += dwa * (mj * (-vij[k]));
-                    }
-                }
-            } else if (need_div) {
+            for (int k = 0; k < DIM; ++k) vij[k] = vi[k] - vj[k];
+        }
+        if (j != i) {
+            const double v_sig = ci + vc.w - 3.0 * dot<DIM>(d, vij) / r;
+            if (v_sig > v_sig_max) v_sig_max = v_sig;
+        }
+        if (SPH == T_GSPH) {
+            if (P.gsph2) {
                 const double c = kc.dwc(r);
-                double dw[DIM];
+                const double uji = __ldg(&rc.thermo[j].x) - ui;
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) dw[a] = d[a] * c;
-                const double wgt = (SPH == T_DISPH) ? mj * uj : mj;
-                div_v -= wgt * dot<DIM>(vij, dw);
-                if (DIM == 2) {
-                    rot_v[0] += (vij[0] * dw[DIM > 1 ? 1 : 0] - vij[DIM > 1 ? 1 : 0] * dw[0]) * wgt;
-                } else if (DIM == 3) {
-                    constexpr int Y = DIM > 1 ? 1 : 0, Z = DIM > 2 ? 2 : 0;
-                    rot_v[0] += (vij[Y] * dw[Z] - vij[Z] * dw[Y]) * wgt;
-                    rot_v[1] += (vij[Z] * dw[0] - vij[0] * dw[Z]) * wgt;
-                    rot_v[2] += (vij[0] * dw[Y] - vij[Y] * dw[0]) * wgt;
+                for (int a = 0; a < DIM; ++a) {
+                    const double dwa = d[a] * c;
+                    dd[a] += dwa * mj;
+                    du[a] += dwa * (mj * uji);
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) dv[k][a] += dwa * (mj * (-vij[k]));
                 }
+            }
+        } else if (need_div) {
+            const double c = kc.dwc(r);
+            double dw[DIM];
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) dw[a] = d[a] * c;
+            const double wgt = (SPH == T_DISPH) ? mj * uj : mj;
+            div_v -= wgt * dot<DIM>(vij, dw);
+            if (DIM == 2) {
+                rot_v[0] += (vij[0] * dw[DIM > 1 ? 1 : 0] - vij[DIM > 1 ? 1 : 0] * dw[0]) * wgt;
+            } else if (DIM == 3) {
+                constexpr int Y = DIM > 1 ? 1 : 0, Z = DIM > 2 ? 2 : 0;
+                rot_v[0] += (vij[Y] * dw[Z] - vij[Z] * dw[Y]) * wgt;
+                rot_v[1] += (vij[Z] * dw[0] - vij[0] * dw[Z]) * wgt;
+                rot_v[2] += (vij[0] * dw[Y] - vij[Y] * dw[0]) * wgt;
             }
         }
     }
 };
 
 template <int DIM, int KT, int SPH>
-__global__ void __launch_bounds__(128)
-k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __restrict__ group_counter,
-                  double * __restrict__ scratch_r, double * __restrict__ scratch_m,
+__global__ void __launch_bounds__(128, 4)
+k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
+                  double * __restrict__ scratch_r, double * __restrict__ scratch_m, int * __restrict__ scratch_j,
                   const double * __restrict__ d_dt, double * __restrict__ d_hpvs,
-                  unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt, const double4 * __restrict__ posm)
+                  unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt)
 {
-    __shared__ double4 s_leaf_all[4][32];
-    double4 * s_leaf = s_leaf_all[threadIdx.x >> 5];
+    __shared__ NWalkSmem s_walk[4];
+    NWalkSmem & sm = s_walk[threadIdx.x >> 5];
     constexpr bool NEED_M = (SPH != T_DISPH);     // DISPH Newton uses unit weights (d_pre_interaction.cpp:208-209)
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     double * lr = scratch_r + (size_t)slot * P.list_cap * 32;
+    int * lj = scratch_j + (size_t)slot * P.list_cap * 32;
     double * lm = NEED_M ? scratch_m + (size_t)slot * P.list_cap * 32 : nullptr;
     const double dt = *d_dt;
     double hpvs_min = 1.7976931348623157e308;
     unsigned int c_evals = 0, c_iters = 0, c_cand = 0, c_ngb = 0, c_nonconv = 0, c_over = 0;   // per lane: fits 32 bits
 
-    for (;;) {
-        int g = 0;
-        if (lane == 0) g = atomicAdd(group_counter, 1);
-        g = __shfl_sync(SPHB_FULL_MASK, g, 0);
-        if (g >= g_end) break;
-        const int i = g * 32 + lane;
-        const bool valid = i < n;
+    int g_first, g_cnt;
+    while (next_group(gt, lane, g_first, g_cnt)) {
+        const int i = g_first + lane;
+        const bool valid = lane < g_cnt;
 
         double ri[DIM], vi[DIM];
         double mass_i = 1.0, dens_old = 1.0, ene_i = 0.0, c_i = 0.0, alpha_i = 0.0;
@@ -264,17 +264,22 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
         const double hs2 = __dmul_rn(hs, hs);
         double h = hs;
 
-        if (P.iterative) {
-            // ---- walk 1: candidates
+        // ---- candidates (src/pre_interaction.cpp:66-71)
+        int ncand;
+        {
             CollectV<DIM, NEED_M> cv{P};
 #pragma unroll
             for (int d = 0; d < DIM; ++d) cv.ri[d] = ri[d];
-            cv.hs = hs; cv.hs2 = hs2; cv.lr = lr; cv.lm = lm; cv.cap = P.list_cap; cv.cnt = 0; cv.lane = lane;
-            warp_walk<true>(t, posm, s_leaf, lane, cv, valid);
-            int ncand = cv.cnt;
-            if (ncand > P.list_cap) { ++c_over; ncand = P.list_cap; }
-            c_cand += valid ? ncand : 0;
-            __syncwarp();
+            cv.hs2 = hs2; cv.lr = lr; cv.lm = lm; cv.lj = lj; cv.cap = P.list_cap; cv.cnt = 0; cv.lane = lane;
+            group_stream<DIM, false>(t, P, rc.posm, nullptr, 0, sm, lane, ri, hs, valid, cv, d_err);
+            ncand = cv.cnt;
+        }
+        if (ncand > P.list_cap) { ++c_over; ncand = P.list_cap; }
+        c_cand += valid ? ncand : 0;
+        __syncwarp();
+        const int ncand_max = __reduce_max_sync(SPHB_FULL_MASK, ncand);
+
+        if (P.iterative) {
             // ---- Newton-Raphson (src/pre_interaction.cpp:227-283)
             const double h0 = hs / P.kernel_ratio;
             const double b = NEED_M ? mass_i * P.ngb / unit_ball<DIM>() : P.ngb / unit_ball<DIM>();
@@ -282,11 +287,12 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
             bool done = !valid, conv = false;
             for (int it = 0; it < 10; ++it) {
                 if (!__any_sync(SPHB_FULL_MASK, !done)) break;
-                if (!done) {
-                    KernelCoef<DIM, KT> kc;
-                    kc.init(h);
-                    double s = 0.0, sd = 0.0;
-                    for (int k = 0; k < ncand; ++k) {
+                KernelCoef<DIM, KT> kc;
+                kc.init(h);
+                double s = 0.0, sd = 0.0;
+                const int nk = done ? 0 : ncand;
+                for (int k = 0; k < ncand_max; ++k) {
+                    if (k < nk) {
                         const double r = lr[k * 32 + lane];
                         if (r < h) {
                             if (NEED_M) {
@@ -300,6 +306,8 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
                             ++c_evals;
                         }
                     }
+                }
+                if (!done) {
                     ++c_iters;
                     const double f = s * powh<DIM>(h) - b;
                     const double df = sd * powh<DIM>(h) + DIM * s * powh_<DIM>(h);
@@ -309,16 +317,14 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
                 }
             }
             if (valid && !conv) { h = h0; ++c_nonconv; }    // logged + fallback, pre_interaction.cpp:277-282
-            __syncwarp();
         }
 
-        // ---- walk 2: density pass (+ Balsara / MUSCL gradients)
-        DensityV<DIM, KT, SPH> dv{P, p};
+        // ---- density pass (+ Balsara / MUSCL gradients) over the candidates with r < h
+        DensityAcc<DIM, KT, SPH> dv{P, p, rc};
         dv.i = i;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) { dv.ri[d] = ri[d]; dv.vi[d] = vi[d]; }
-        dv.hs2 = hs2; dv.h = h; dv.reach = fmin(h, hs); dv.ci = c_i; dv.ui = ene_i;
-        dv.hit2 = fmin(hs2, h * h * (1.0 + 1e-14));
+        dv.ci = c_i; dv.ui = ene_i;
         dv.kc.init(h);
         dv.need_div = (SPH != T_GSPH) && ((P.use_balsara && DIM != 1) || P.use_tdav);
         dv.dens = dv.dh_dens = dv.n_i = dv.dh_n = dv.pres = dv.dh_pres = 0.0;
@@ -331,22 +337,44 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
 #pragma unroll
             for (int k = 0; k < DIM; ++k) dv.dv[k][a] = 0.0;
         }
-        warp_walk<true>(t, posm, s_leaf, lane, dv, valid);
+        {
+            // every lane skips ahead to its next candidate with r < h (the `break` of the sorted loop,
+            // src/pre_interaction.cpp:87-91), then all lanes run the pair body together
+            const int nk = valid ? ncand : 0;
+            int k = 0;
+            for (;;) {
+                double r = 0.0;
+                while (k < nk) {
+                    r = lr[k * 32 + lane];
+                    if (r < h) break;
+                    ++k;
+                }
+                const bool act = k < nk;
+                if (!__any_sync(SPHB_FULL_MASK, act)) break;
+                if (act) {
+                    dv.pair(lj[k * 32 + lane], r);
+                    ++k;
+                }
+            }
+        }
 
         if (valid) {
             const double dens_i = dv.dens;
-            double pres_i, div_norm;
+            double pres_i, div_norm, gradh_i = 0.0, bal_i = 1.0, alpha_new = alpha_i;
             if (SPH == T_SSPH) {
                 pres_i = (P.gamma - 1.0) * dens_i * ene_i;
-                p.gradh[i] = 1.0 / (1.0 + h / (DIM * dens_i) * dv.dh_dens);
+                gradh_i = 1.0 / (1.0 + h / (DIM * dens_i) * dv.dh_dens);
+                p.gradh[i] = gradh_i;
                 div_norm = 1.0 / dens_i;
             } else if (SPH == T_DISPH) {
                 pres_i = (P.gamma - 1.0) * dv.pres;
-                p.gradh[i] = h / (DIM * dv.n_i) * dv.dh_pres / (1.0 + h / (DIM * dv.n_i) * dv.dh_n);
+                gradh_i = h / (DIM * dv.n_i) * dv.dh_pres / (1.0 + h / (DIM * dv.n_i) * dv.dh_n);
+                p.gradh[i] = gradh_i;
                 div_norm = (P.gamma - 1.0) / pres_i;
             } else {
                 pres_i = (P.gamma - 1.0) * dens_i * ene_i;
                 div_norm = 0.0;
+                gradh_i = p.gradh[i];
             }
             p.sml[i] = h;
             p.dens[i] = dens_i;
@@ -366,6 +394,7 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
                         for (int k = 0; k < DIM; ++k) p.grad_v[k][a][i] = dv.dv[k][a] * rho_inv;
                     }
                 }
+                bal_i = p.balsara[i];
             } else if (P.use_balsara && DIM != 1) {
                 const double div_v = (SPH == T_SSPH) ? dv.div_v / dens_i : dv.div_v * div_norm;
                 double rot_abs;
@@ -377,19 +406,31 @@ k_pre_interaction(PSoA p, TreeDev t, DevParams P, int n, int g_end, int * __rest
                     for (int a = 0; a < 3; ++a) rr[a] = (SPH == T_SSPH) ? dv.rot_v[a] / dens_i : dv.rot_v[a] * div_norm;
                     rot_abs = sqrt(rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2]);
                 }
-                p.balsara[i] = fabs(div_v) / (fabs(div_v) + rot_abs + 1e-4 * c_i / h);
+                bal_i = fabs(div_v) / (fabs(div_v) + rot_abs + 1e-4 * c_i / h);
+                p.balsara[i] = bal_i;
                 if (P.use_tdav) {
                     const double tau_inv = P.epsilon_av * c_i / h;
                     const double dalpha = (-(alpha_i - P.alpha_min) * tau_inv + fmax(-div_v, 0.0) * (P.alpha_max - alpha_i)) * dt;
-                    p.alpha[i] = alpha_i + dalpha;
+                    alpha_new = alpha_i + dalpha;
+                    p.alpha[i] = alpha_new;
                 }
-            } else if (P.use_tdav) {
-                const double div_v = (SPH == T_SSPH) ? dv.div_v / dens_i : dv.div_v * div_norm;
-                const double tau_inv = P.epsilon_av * c_i / h;
-                const double s_i = fmax(-div_v, 0.0);
-                p.alpha[i] = (alpha_i + dt * tau_inv * P.alpha_min + s_i * dt * P.alpha_max) / (1.0 + dt * tau_inv + s_i * dt);
+            } else {
+                bal_i = p.balsara[i];
+                if (P.use_tdav) {
+                    const double div_v = (SPH == T_SSPH) ? dv.div_v / dens_i : dv.div_v * div_norm;
+                    const double tau_inv = P.epsilon_av * c_i / h;
+                    const double s_i = fmax(-div_v, 0.0);
+                    alpha_new = (alpha_i + dt * tau_inv * P.alpha_min + s_i * dt * P.alpha_max) / (1.0 + dt * tau_inv + s_i * dt);
+                    p.alpha[i] = alpha_new;
+                }
             }
+            // gather records of the force pass (u stays as packed: other warps may be reading it)
+            double * th = reinterpret_cast<double *>(&rc.thermo[i]);
+            th[1] = h;
+            *reinterpret_cast<double2 *>(th + 2) = make_double2(dens_i, pres_i);
+            rc.av[i] = make_double4(gradh_i, alpha_new, bal_i, 0.0);
         }
+        __syncwarp();
     }
 
     hpvs_min = warp_min(hpvs_min);
@@ -456,9 +497,28 @@ __device__ __forceinline__ void hll(const double (&left)[4], const double (&righ
     pstar = (c1 * c5 - c2 * c4) * c3;
 }
 
+// pair set of lane i: {j : 0 < r < max(h_i, h_j)} (src/fluid_force.cpp:62; the reference's candidate
+// test r2 < max(h_i, kernel_size(leaf))^2, src/bhtree.cpp:255-256, is implied by it) -> j column
+template <int DIM>
+struct PairCollectV {
+    const DevParams & P;
+    double ri[DIM], h_i;
+    int * lj;
+    int cap, cnt, lane;
+    __device__ __forceinline__ void hit(int j, const double4 & pj, double h_j)
+    {
+        double d[DIM];
+        rij_from4<DIM>(P, ri, pj, d);
+        const double r = sqrt(abs2_exact<DIM>(d));
+        if (r >= fmax(h_i, h_j) || r == 0.0) return;
+        if (cnt < cap) lj[cnt * 32 + lane] = j;
+        ++cnt;
+    }
+};
+
 template <int DIM, int KT, int SPH>
-struct ForceV {
-    const DevParams & P; const PSoA & p;
+struct ForceAcc {
+    const DevParams & P; const PSoA & p; const Recs & rc;
     int i;
     double dt;
     double ri[DIM], vi[DIM], h_i, m_i, dens_i, pres_i, gradh_i, alpha_i, bal_i, c_i, u_i;
@@ -468,210 +528,238 @@ struct ForceV {
     double m_u_inv;         // DISPH: 1/(m_i u_i)
     KernelCoef<DIM, KT> ki;
     double acc[DIM], dene;
-    unsigned int pairs;
 
-    __device__ __forceinline__ bool open(const NodeRec & nd)
+    __device__ __forceinline__ void pair(int j)
     {
-        const double h = fmax(h_i, nd.e);                           // src/bhtree.cpp:237
-        return node_in_reach<DIM>(P, nd, ri, h);
-    }
-    __device__ __forceinline__ void leaf(const NodeRec & nd, int base, int m, const double4 * sl)
-    {
-        const double h = fmax(h_i, nd.e);
-        const double h2 = __dmul_rn(h, h);
-        unsigned hits = 0;
-#pragma unroll 4
-        for (int k = 0; k < m; ++k) {
-            double d[DIM];
-            rij_from4<DIM>(P, ri, sl[k], d);
-            const double r2 = abs2_exact<DIM>(d);
-            if (r2 < h2) hits |= 1u << k;                           // src/bhtree.cpp:255-256
-        }
-        while (hits) {
-            const int kb = __ffs(hits) - 1;
-            const int j = base + kb;
-            hits &= hits - 1;
-            const double4 pj = sl[kb];
-            double d[DIM];
-            rij_from4<DIM>(P, ri, pj, d);
-            const double r2 = abs2_exact<DIM>(d);
-            const double h_j = p.sml[j];
-            const double r = sqrt(r2);
-            if (r >= fmax(h_i, h_j) || r == 0.0) continue;          // src/fluid_force.cpp:62
-            ++pairs;
-            KernelCoef<DIM, KT> kj;
-            kj.init(h_j);
-            const double cwi = ki.dwc(r), cwj = kj.dwc(r);
-            double dw_i[DIM], dw_j[DIM], vij[DIM], vj[DIM];
-            load_vec<DIM>(p.vel, j, vj);
+        const double4 pj = ldg4(&rc.posm[j]);
+        const double4 vc = ldg4(&rc.velc[j]);
+        const double4 th = ldg4(&rc.thermo[j]);          // {u, h, dens, pres}
+        double d[DIM];
+        rij_from4<DIM>(P, ri, pj, d);
+        const double r = sqrt(abs2_exact<DIM>(d));
+        const double h_j = th.y;
+        KernelCoef<DIM, KT> kj;
+        kj.init(h_j);
+        const double cwi = ki.dwc(r), cwj = kj.dwc(r);
+        double dw_i[DIM], dw_j[DIM], vij[DIM], vj[DIM];
+        vec_from4<DIM>(vc, vj);
 #pragma unroll
-            for (int a = 0; a < DIM; ++a) { dw_i[a] = d[a] * cwi; dw_j[a] = d[a] * cwj; vij[a] = vi[a] - vj[a]; }
-            const double m_j = pj.w;
-            const double dens_j = p.dens[j], pres_j = p.pres[j];
+        for (int a = 0; a < DIM; ++a) { dw_i[a] = d[a] * cwi; dw_j[a] = d[a] * cwj; vij[a] = vi[a] - vj[a]; }
+        const double m_j = pj.w;
+        const double dens_j = th.z, pres_j = th.w;
+        const double c_j = vc.w;
 
-            if (SPH == T_GSPH) {
-                const double c_j = p.sound[j];
-                const double r_inv = 1.0 / r;
-                double e[DIM];
+        if (SPH == T_GSPH) {
+            const double r_inv = 1.0 / r;
+            double e[DIM];
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) e[a] = d[a] * r_inv;
-                const double ve_i = dot<DIM>(vi, e);
-                const double ve_j = dot<DIM>(vj, e);
-                double vstar, pstar;
-                if (P.gsph2) {
-                    // Murante et al. (2011), src/gsph/g_fluid_force.cpp:96-134
-                    double right[4], left[4];
-                    const double delta_i = 0.5 * (1.0 - c_i * dt * r_inv);
-                    const double delta_j = 0.5 * (1.0 - c_j * dt * r_inv);
-                    const double dv_ij = ve_i - ve_j;
-                    double dvi[DIM], dvj[DIM], gdj[DIM], gpj[DIM];
+            for (int a = 0; a < DIM; ++a) e[a] = d[a] * r_inv;
+            const double ve_i = dot<DIM>(vi, e);
+            const double ve_j = dot<DIM>(vj, e);
+            double vstar, pstar;
+            if (P.gsph2) {
+                // Murante et al. (2011), src/gsph/g_fluid_force.cpp:96-134
+                double right[4], left[4];
+                const double delta_i = 0.5 * (1.0 - c_i * dt * r_inv);
+                const double delta_j = 0.5 * (1.0 - c_j * dt * r_inv);
+                const double dv_ij = ve_i - ve_j;
+                double dvi[DIM], dvj[DIM], gdj[DIM], gpj[DIM];
 #pragma unroll
-                    for (int k = 0; k < DIM; ++k) {
-                        double gvj[DIM];
+                for (int k = 0; k < DIM; ++k) {
+                    double gvj[DIM];
 #pragma unroll
-                        for (int a = 0; a < DIM; ++a) gvj[a] = p.grad_v[k][a][j];
-                        dvi[k] = dot<DIM>(gvi[k], e);
-                        dvj[k] = dot<DIM>(gvj, e);
-                    }
-#pragma unroll
-                    for (int a = 0; a < DIM; ++a) { gdj[a] = p.grad_d[a][j]; gpj[a] = p.grad_p[a][j]; }
-                    const double dve_i = dot<DIM>(dvi, e) * r;
-                    const double dve_j = dot<DIM>(dvj, e) * r;
-                    right[0] = ve_i - van_leer(dv_ij, dve_i) * delta_i;
-                    left[0] = ve_j + van_leer(dv_ij, dve_j) * delta_j;
-                    const double dd_ij = dens_i - dens_j;
-                    const double dd_i = dot<DIM>(gdi, e) * r;
-                    const double dd_j = dot<DIM>(gdj, e) * r;
-                    right[1] = dens_i - van_leer(dd_ij, dd_i) * delta_i;
-                    left[1] = dens_j + van_leer(dd_ij, dd_j) * delta_j;
-                    const double dp_ij = pres_i - pres_j;
-                    const double dp_i = dot<DIM>(gpi, e) * r;
-                    const double dp_j = dot<DIM>(gpj, e) * r;
-                    right[2] = pres_i - van_leer(dp_ij, dp_i) * delta_i;
-                    left[2] = pres_j + van_leer(dp_ij, dp_j) * delta_j;
-                    right[3] = sqrt(P.gamma * right[2] / right[1]);
-                    left[3] = sqrt(P.gamma * left[2] / left[1]);
-                    hll(left, right, pstar, vstar);
-                } else {
-                    const double right[4] = {ve_i, dens_i, pres_i, c_i};
-                    const double left[4] = {ve_j, dens_j, pres_j, c_j};
-                    hll(left, right, pstar, vstar);
+                    for (int a = 0; a < DIM; ++a) gvj[a] = p.grad_v[k][a][j];
+                    dvi[k] = dot<DIM>(gvi[k], e);
+                    dvj[k] = dot<DIM>(gvj, e);
                 }
-                const double rho2_inv_j = 1.0 / (dens_j * dens_j);
-                double fdotv = 0.0;
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    const double f = dw_i[a] * (m_j * pstar * pp_i) + dw_j[a] * (m_j * pstar * rho2_inv_j);
-                    acc[a] -= f;
-                    fdotv += f * (e[a] * vstar - vi[a]);
-                }
-                dene -= fdotv;
+                for (int a = 0; a < DIM; ++a) { gdj[a] = p.grad_d[a][j]; gpj[a] = p.grad_p[a][j]; }
+                const double dve_i = dot<DIM>(dvi, e) * r;
+                const double dve_j = dot<DIM>(dvj, e) * r;
+                right[0] = ve_i - van_leer(dv_ij, dve_i) * delta_i;
+                left[0] = ve_j + van_leer(dv_ij, dve_j) * delta_j;
+                const double dd_ij = dens_i - dens_j;
+                const double dd_i = dot<DIM>(gdi, e) * r;
+                const double dd_j = dot<DIM>(gdj, e) * r;
+                right[1] = dens_i - van_leer(dd_ij, dd_i) * delta_i;
+                left[1] = dens_j + van_leer(dd_ij, dd_j) * delta_j;
+                const double dp_ij = pres_i - pres_j;
+                const double dp_i = dot<DIM>(gpi, e) * r;
+                const double dp_j = dot<DIM>(gpj, e) * r;
+                right[2] = pres_i - van_leer(dp_ij, dp_i) * delta_i;
+                left[2] = pres_j + van_leer(dp_ij, dp_j) * delta_j;
+                right[3] = sqrt(P.gamma * right[2] / right[1]);
+                left[3] = sqrt(P.gamma * left[2] / left[1]);
+                hll(left, right, pstar, vstar);
             } else {
-                const double c_j = p.sound[j];
-                const double vr = dot<DIM>(vij, d);
-                const double pi_ij = art_visc(vr, r, c_i, c_j, alpha_i, p.alpha[j], bal_i, p.balsara[j], dens_i, dens_j);
-                double dw_ij[DIM];
-#pragma unroll
-                for (int a = 0; a < DIM; ++a) dw_ij[a] = (dw_i[a] + dw_j[a]) * 0.5;
-                const double u_j = p.ene[j];
-                double dene_ac = 0.0;
-                if (P.use_ac) {
-                    // src/fluid_force.cpp:108-116
-                    const double v_sig = P.use_gravity ? fabs(vr / r) : sqrt(2.0 * fabs(pres_i - pres_j) / (dens_i + dens_j));
-                    dene_ac = P.alpha_ac * m_j * v_sig * (u_i - u_j) * dot<DIM>(dw_ij, d) / r;
-                }
-                double ti, tj, ei;
-                if (SPH == T_SSPH) {
-                    // src/fluid_force.cpp:78-79
-                    ti = m_j * (pp_i + 0.5 * pi_ij);
-                    tj = m_j * (pres_j / (dens_j * dens_j) * p.gradh[j] + 0.5 * pi_ij);
-                    ei = m_j * pp_i;
-                } else {
-                    // src/disph/d_fluid_force.cpp:70-79
-                    const double f_ij = 1.0 - gradh_i / (m_j * u_j);
-                    const double f_ji = 1.0 - p.gradh[j] * m_u_inv;
-                    const double u_per_pres_j = u_j / pres_j;
-                    ti = m_j * (pp_i * u_j * f_ij + 0.5 * pi_ij);
-                    tj = m_j * (g2u_i * u_per_pres_j * f_ji + 0.5 * pi_ij);
-                    ei = m_j * pp_i * u_j * f_ij;
-                }
-#pragma unroll
-                for (int a = 0; a < DIM; ++a) acc[a] -= dw_i[a] * ti + dw_j[a] * tj;
-                dene += ei * dot<DIM>(vij, dw_i) + 0.5 * m_j * pi_ij * dot<DIM>(vij, dw_ij) + dene_ac;
+                const double right[4] = {ve_i, dens_i, pres_i, c_i};
+                const double left[4] = {ve_j, dens_j, pres_j, c_j};
+                hll(left, right, pstar, vstar);
             }
+            const double rho2_inv_j = 1.0 / (dens_j * dens_j);
+            double fdotv = 0.0;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) {
+                const double f = dw_i[a] * (m_j * pstar * pp_i) + dw_j[a] * (m_j * pstar * rho2_inv_j);
+                acc[a] -= f;
+                fdotv += f * (e[a] * vstar - vi[a]);
+            }
+            dene -= fdotv;
+        } else {
+            const double4 avj = ldg4(&rc.av[j]);          // {gradh, alpha, balsara, -}
+            const double vr = dot<DIM>(vij, d);
+            const double pi_ij = art_visc(vr, r, c_i, c_j, alpha_i, avj.y, bal_i, avj.z, dens_i, dens_j);
+            double dw_ij[DIM];
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) dw_ij[a] = (dw_i[a] + dw_j[a]) * 0.5;
+            const double u_j = th.x;
+            double dene_ac = 0.0;
+            if (P.use_ac) {
+                // src/fluid_force.cpp:108-116
+                const double v_sig = P.use_gravity ? fabs(vr / r) : sqrt(2.0 * fabs(pres_i - pres_j) / (dens_i + dens_j));
+                dene_ac = P.alpha_ac * m_j * v_sig * (u_i - u_j) * dot<DIM>(dw_ij, d) / r;
+            }
+            double ti, tj, ei;
+            if (SPH == T_SSPH) {
+                // src/fluid_force.cpp:78-79
+                ti = m_j * (pp_i + 0.5 * pi_ij);
+                tj = m_j * (pres_j / (dens_j * dens_j) * avj.x + 0.5 * pi_ij);
+                ei = m_j * pp_i;
+            } else {
+                // src/disph/d_fluid_force.cpp:70-79
+                const double f_ij = 1.0 - gradh_i / (m_j * u_j);
+                const double f_ji = 1.0 - avj.x * m_u_inv;
+                const double u_per_pres_j = u_j / pres_j;
+                ti = m_j * (pp_i * u_j * f_ij + 0.5 * pi_ij);
+                tj = m_j * (g2u_i * u_per_pres_j * f_ji + 0.5 * pi_ij);
+                ei = m_j * pp_i * u_j * f_ij;
+            }
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) acc[a] -= dw_i[a] * ti + dw_j[a] * tj;
+            dene += ei * dot<DIM>(vij, dw_i) + 0.5 * m_j * pi_ij * dot<DIM>(vij, dw_ij) + dene_ac;
         }
     }
 };
 
 template <int DIM, int KT, int SPH>
-__global__ void __launch_bounds__(128)
-k_fluid_force(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const double * __restrict__ d_dt,
-              Counters * __restrict__ cnt, const double4 * __restrict__ posm)
+__global__ void __launch_bounds__(128, 4)
+k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
+              int * __restrict__ scratch_j, const double * __restrict__ d_dt,
+              unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt)
 {
-    __shared__ double4 s_leaf[4][32];
+    __shared__ NWalkSmem s_walk[4];
+    NWalkSmem & sm = s_walk[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int i = i_begin + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
-    const bool valid = i < i_end;
-    ForceV<DIM, KT, SPH> v{P, p};
-    v.i = i;
-    v.dt = *d_dt;
-    v.pairs = 0;
-    v.dene = 0.0;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int * lj = scratch_j + (size_t)slot * P.list_cap * 32;
+    const double dt = *d_dt;
+    unsigned int c_pairs = 0, c_over = 0;
+
+    int g_first, g_cnt;
+    while (next_group(gt, lane, g_first, g_cnt)) {
+        const int i = g_first + lane;
+        const bool valid = lane < g_cnt;
+
+        ForceAcc<DIM, KT, SPH> v{P, p, rc};
+        v.i = i;
+        v.dt = dt;
+        v.dene = 0.0;
 #pragma unroll
-    for (int a = 0; a < DIM; ++a) { v.acc[a] = 0.0; v.ri[a] = 0.0; v.vi[a] = 0.0; }
-    v.h_i = 1.0; v.m_i = 1.0; v.dens_i = 1.0; v.pres_i = 1.0; v.gradh_i = 0.0; v.alpha_i = 0.0; v.bal_i = 0.0; v.c_i = 0.0; v.u_i = 1.0;
-    if (valid) {
-        load_vec<DIM>(p.pos, i, v.ri);
-        load_vec<DIM>(p.vel, i, v.vi);
-        v.h_i = p.sml[i]; v.m_i = p.mass[i]; v.dens_i = p.dens[i]; v.pres_i = p.pres[i];
-        v.c_i = p.sound[i]; v.u_i = p.ene[i];
-        if (SPH != T_GSPH) { v.gradh_i = p.gradh[i]; v.alpha_i = p.alpha[i]; v.bal_i = p.balsara[i]; }
-        if (SPH == T_GSPH && P.gsph2) {
+        for (int a = 0; a < DIM; ++a) { v.acc[a] = 0.0; v.ri[a] = 0.0; v.vi[a] = 0.0; }
+        v.h_i = 1.0; v.m_i = 1.0; v.dens_i = 1.0; v.pres_i = 1.0; v.gradh_i = 0.0; v.alpha_i = 0.0; v.bal_i = 0.0; v.c_i = 0.0; v.u_i = 1.0;
+        if (valid) {
+            load_vec<DIM>(p.pos, i, v.ri);
+            load_vec<DIM>(p.vel, i, v.vi);
+            v.h_i = p.sml[i]; v.m_i = p.mass[i]; v.dens_i = p.dens[i]; v.pres_i = p.pres[i];
+            v.c_i = p.sound[i]; v.u_i = p.ene[i];
+            if (SPH != T_GSPH) { v.gradh_i = p.gradh[i]; v.alpha_i = p.alpha[i]; v.bal_i = p.balsara[i]; }
+            if (SPH == T_GSPH && P.gsph2) {
 #pragma unroll
-            for (int a = 0; a < DIM; ++a) {
-                v.gdi[a] = p.grad_d[a][i]; v.gpi[a] = p.grad_p[a][i];
+                for (int a = 0; a < DIM; ++a) {
+                    v.gdi[a] = p.grad_d[a][i]; v.gpi[a] = p.grad_p[a][i];
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) v.gvi[k][a] = p.grad_v[k][a][i];
+                    for (int k = 0; k < DIM; ++k) v.gvi[k][a] = p.grad_v[k][a][i];
+                }
             }
         }
-    }
-    if (SPH == T_SSPH) {
-        v.pp_i = v.pres_i / (v.dens_i * v.dens_i) * v.gradh_i;
-    } else if (SPH == T_DISPH) {
-        v.g2u_i = (P.gamma - 1.0) * (P.gamma - 1.0) * v.u_i;
-        v.pp_i = v.g2u_i / v.pres_i;
-        v.m_u_inv = 1.0 / (v.m_i * v.u_i);
-    } else {
-        v.pp_i = 1.0 / (v.dens_i * v.dens_i);
-    }
-    v.ki.init(v.h_i);
-    warp_walk<false>(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
-    if (valid) {
+        if (SPH == T_SSPH) {
+            v.pp_i = v.pres_i / (v.dens_i * v.dens_i) * v.gradh_i;
+        } else if (SPH == T_DISPH) {
+            v.g2u_i = (P.gamma - 1.0) * (P.gamma - 1.0) * v.u_i;
+            v.pp_i = v.g2u_i / v.pres_i;
+            v.m_u_inv = 1.0 / (v.m_i * v.u_i);
+        } else {
+            v.pp_i = 1.0 / (v.dens_i * v.dens_i);
+        }
+        v.ki.init(v.h_i);
+
+        // ---- symmetric pair search
+        int npair;
+        {
+            PairCollectV<DIM> cv{P};
 #pragma unroll
-        for (int a = 0; a < DIM; ++a) p.acc[a][i] = v.acc[a];
-        p.dene[i] = v.dene;
+            for (int a = 0; a < DIM; ++a) cv.ri[a] = v.ri[a];
+            cv.h_i = v.h_i; cv.lj = lj; cv.cap = P.list_cap; cv.cnt = 0; cv.lane = lane;
+            group_stream<DIM, true>(t, P, rc.posm, reinterpret_cast<const double *>(rc.thermo) + 1, 4, sm, lane, v.ri, v.h_i, valid, cv, d_err);
+            npair = cv.cnt;
+        }
+        if (npair > P.list_cap) { ++c_over; npair = P.list_cap; }
+        if (!valid) npair = 0;
+        c_pairs += npair;
+        __syncwarp();
+        const int npair_max = __reduce_max_sync(SPHB_FULL_MASK, npair);
+        // ---- pair bodies, all lanes together
+        for (int k = 0; k < npair_max; ++k) {
+            if (k < npair) v.pair(lj[k * 32 + lane]);
+        }
+        if (valid) {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) p.acc[a][i] = v.acc[a];
+            p.dene[i] = v.dene;
+        }
+        __syncwarp();
     }
     if (cnt) {
-        const unsigned long long s = warp_sum_u64(valid ? (unsigned long long)v.pairs : 0ull);
+        const unsigned long long s = warp_sum_u64(c_pairs);
         if (lane == 0) atomicAdd(&cnt->force_pairs, s);
     }
+    const unsigned long long ov = warp_sum_u64(c_over);
+    if (lane == 0 && ov) atomicAdd(&d_err[1], ov);
 }
 
 // =================================================================================================
 // GravityForce::calculation -> BHNode::calc_force, src/bhtree.cpp:301-331
 // =================================================================================================
-// The walk visits the union of the 32 lanes' reference walks; each lane applies the reference's own
-// opening test (edge^2 > theta^2 |r_i - com|^2) to the nodes it is still descending, so the set of
-// cells it accepts and leaves it opens is exactly BHNode::calc_force's for that particle.  The
-// interactions themselves are deferred so that lanes do them together although they accept /
-// open at different nodes:
+// Group walk, breadth-first with one lane per node (as in sphb_walk.cuh), that reproduces the
+// reference's PER-PARTICLE opening decisions exactly:
+//   * every stack entry carries the mask of lanes (particles) that opened all its ancestors;
+//   * a node is first classified against the group's bounding box: if even the nearest point of the
+//     box accepts it (edge^2 <= theta^2 d_min^2) every lane of the mask accepts it; if even the
+//     farthest point opens it, every lane opens it; both with a safety margin, so these decisions
+//     coincide with the per-particle test of src/bhtree.cpp:308;
+//   * the remaining ("mixed") nodes are tested lane by lane with the reference's own expression,
+//     which splits the mask into the lanes that accept and the lanes that descend.
+// The set of cells a particle accepts and of leaves it opens is therefore exactly
+// BHNode::calc_force's.  The interactions themselves are deferred so that lanes do them together:
 //   * accepted cells go to a 32-entry chunk staged in shared memory (mass centre + mass) with a
-//     per-lane accept mask; when the chunk is full every lane runs over ITS mask (popcounts are
-//     close, so the monopole body runs convergent);
+//     per-lane accept mask; when the chunk is full every lane runs over ITS mask;
 //   * opened leaves go to a per-lane queue of (first, count); when any lane's queue is full, every
 //     lane runs one flattened loop over all particles of its queued leaves (packed x,y,z,m + 2/h
 //     read through L1; lanes of a warp are Morton neighbours and share these lines).
-constexpr int GRAV_LQ = 8;      // leaf queue depth per lane
+constexpr int GRAV_LQ = 8;        // leaf queue depth per lane
+constexpr int GV_STACK = 704;     // node stack entries per warp (<= 28 stay behind per tree level, see pop_load)
+
+struct GravSmem {
+    int2     stack[GV_STACK];           // {child0 | (nchild - 1) << 29, lane mask}: the children of an opened node
+    int2     expand[32];                // {node, lane mask} of the batch being fetched
+    double4  pc[32];                    // accepted cells of the current chunk
+    double4  mx[32];                    // mixed nodes of the current batch: mass centre + mass
+    double   me2[32];                   //   edge^2
+    int4     minfo[32];                 //   {child0, nchild, first, count}
+    unsigned mmask[32];                 //   lane mask
+    int2     lq[GRAV_LQ][32];           // per-lane queue of opened leaves
+    unsigned near[GRAV_LQ][32];         // softened pairs of a queued leaf
+};
 
 // Softening functions with the divisions by constants turned into products (soft_fg in
 // sphb_math.cuh keeps the literal form for the direct-sum checker kernel).
@@ -693,16 +781,20 @@ __device__ __forceinline__ void soft_fg_fast(double r, double rinv, double einv,
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(128)
-k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const double4 * __restrict__ posm,
-          const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, Counters * __restrict__ cnt)
+__global__ void __launch_bounds__(128, 4)
+k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restrict__ posm,
+          const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, Counters * __restrict__ cnt,
+          unsigned long long * __restrict__ d_err)
 {
-    __shared__ double4 s_pc[4][32];
-    __shared__ int2 s_lq[4][GRAV_LQ][32];
-    __shared__ unsigned s_near[4][GRAV_LQ][32];
+    __shared__ GravSmem s_all[4];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int i = i_begin + (blockIdx.x * (blockDim.x >> 5) + w) * 32 + lane;
-    const bool valid = i < i_end;
+    GravSmem & sm = s_all[w];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long tot_pp = 0, tot_pc = 0, tot_visit = 0;
+    int g_first, g_cnt;
+    while (next_group(gt, lane, g_first, g_cnt)) {
+    const int i = g_first + lane;
+    const bool valid = lane < g_cnt;
     double ri[DIM], acc[DIM], phi = 0.0, h_i = 1.0;          // phi = 0: src/bhtree.cpp:130
 #pragma unroll
     for (int a = 0; a < DIM; ++a) { ri[a] = 0.0; acc[a] = 0.0; }
@@ -716,7 +808,10 @@ k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const d
     unsigned int n_pp = 0, n_pc = 0, n_visit = 0;             // per lane: fit 32 bits
     unsigned pc_mask = 0;
     int npc = 0, nlq = 0;
-    double4 * const my_pc = s_pc[w];
+
+    double bc[DIM], bh[DIM];
+    group_box<DIM>(ri, valid, bc, bh);
+    const unsigned vmask = __ballot_sync(SPHB_FULL_MASK, valid);
 
     // accepted cells of the current chunk: monopole, src/bhtree.cpp:326-330
     auto flush_pc = [&]() {
@@ -725,7 +820,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const d
         while (mm) {
             const int e = __ffs(mm) - 1;
             mm &= mm - 1;
-            const double4 c = my_pc[e];
+            const double4 c = sm.pc[e];
             double d[DIM];
             rij_from4<DIM>(P, ri, c, d);
             const double d2 = dot<DIM>(d, d);
@@ -749,7 +844,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const d
         int q = 0, k = 0;
         int2 cur = make_int2(0, 0);
         unsigned near = 0;
-        if (nlq > 0) cur = s_lq[w][0][lane];
+        if (nlq > 0) cur = sm.lq[0][lane];
         while (q < nlq) {
             const int j = cur.x + k;
             const double4 pj = ldg4(&posm[j]);
@@ -769,18 +864,18 @@ k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const d
             }
             ++n_pp;
             if (++k == cur.y) {
-                s_near[w][q][lane] = near;
+                sm.near[q][lane] = near;
                 near = 0;
                 k = 0;
                 ++q;
-                if (q < nlq) cur = s_lq[w][q][lane];
+                if (q < nlq) cur = sm.lq[q][lane];
             }
         }
         q = 0;
         near = 0;
         int first = 0;
         for (;;) {
-            while (near == 0 && q < nlq) { near = s_near[w][q][lane]; first = s_lq[w][q][lane].x; ++q; }
+            while (near == 0 && q < nlq) { near = sm.near[q][lane]; first = sm.lq[q][lane].x; ++q; }
             if (near == 0) break;
             const int j = first + __ffs(near) - 1;
             near &= near - 1;
@@ -802,44 +897,191 @@ k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const d
         }
         nlq = 0;
     };
+    // lanes with `me` queue the leaf [first, first + count) in 32-particle pieces (leaves deeper than
+    // 32 particles exist at the maximum tree level)
+    auto queue_leaf = [&](bool me, int first, int count) {
+        const int last = first + count;
+        for (int base = first; base < last; base += 32) {
+            if (me) { sm.lq[nlq][lane] = make_int2(base, min(32, last - base)); ++nlq; }
+            if (__any_sync(SPHB_FULL_MASK, nlq == GRAV_LQ)) flush_pp();
+        }
+    };
 
-    int idx = 0;
-    int resume = valid ? 0 : INT_MAX;
-    const int n_nodes = t.n_nodes;
-    while (idx < n_nodes) {
-        const NodeRec nd = load_node(t.ng, idx);          // x,y,z = mass centre, w = mass, e = edge^2
-        bool open = false, accept = false;
-        if (idx >= resume) {
-            ++n_visit;
-            double c[DIM], d[DIM];
-            c[0] = nd.x;
-            if (DIM >= 2) c[DIM >= 2 ? 1 : 0] = nd.y;
-            if (DIM >= 3) c[DIM >= 3 ? 2 : 0] = nd.z;
-            calc_r_ij<DIM>(P, ri, c, d);
-            const double d2 = abs2_exact<DIM>(d);
-            if (nd.e > __dmul_rn(P.theta2, d2)) open = true;           // src/bhtree.cpp:308
-            else { accept = true; resume = idx + nd.skip; }
+    // ---- node stack and the batch held in registers.  A stack entry stands for ALL children of an
+    // opened node (they are contiguous), so a batch of <= 32 nodes pushes <= 32 entries and pops >= 32 / NCH:
+    // at most 28 entries stay behind per tree level, GV_STACK covers the deepest tree (21 levels).
+    int top = 1;
+    if (lane == 0) sm.stack[0] = make_int2(0, (int)vmask);          // the root alone: child0 = 0, nchild = 1
+    __syncwarp();
+    int k = 0, node = -1;
+    unsigned mask = 0;
+    double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0;
+    auto pop_load = [&]() {
+        const int ne = min(top, 32);
+        int2 ent = make_int2(0, 0);
+        int nc = 0;
+        if (lane < ne) { ent = sm.stack[top - 1 - lane]; nc = (int)((unsigned)ent.x >> 29) + 1; }
+        int incl = nc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(SPHB_FULL_MASK, incl, o);
+            if (lane >= o) incl += y;
         }
-        const unsigned acc_b = __ballot_sync(SPHB_FULL_MASK, accept);
-        const bool any_open = __any_sync(SPHB_FULL_MASK, open);
-        if (acc_b) {
-            if (accept) pc_mask |= 1u << npc;
-            if (lane == 0) my_pc[npc] = make_double4(nd.x, nd.y, nd.z, nd.w);      // node record is warp-uniform
-            if (++npc == 32) flush_pc();
+        const int m = __popc(__ballot_sync(SPHB_FULL_MASK, lane < ne && incl <= 32));   // entries taken (a prefix)
+        k = m > 0 ? __shfl_sync(SPHB_FULL_MASK, incl, m - 1) : 0;
+        if (lane < m) {
+            const int c0 = ent.x & 0x1fffffff;
+            for (int ci = 0; ci < nc; ++ci) sm.expand[incl - nc + ci] = make_int2(c0 + ci, ent.y);
         }
-        if (any_open) {
-            if (nd.leaf) {
-                // leaves deeper than 32 particles (max tree level) are queued in 32-particle pieces
-                const int last = nd.first + nd.count;
-                for (int base = nd.first; base < last; base += 32) {
-                    if (open) { s_lq[w][nlq][lane] = make_int2(base, min(32, last - base)); ++nlq; }
-                    if (__any_sync(SPHB_FULL_MASK, nlq == GRAV_LQ)) flush_pp();
+        __syncwarp();
+        node = -1;
+        mask = 0;
+        if (lane < k) {
+            const int2 e = sm.expand[lane];
+            node = e.x;
+            mask = (unsigned)e.y;
+            const double2 * q = t.ng + (size_t)node * 4;
+            q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2);
+        }
+        top -= m;
+        __syncwarp();
+    };
+    double cmax = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) cmax = fmax(cmax, fabs(bc[d]) + bh[d]);
+
+    pop_load();
+    for (;;) {
+        if (k == 0) {
+            if (top == 0) break;
+            pop_load();
+        }
+        // ---- classify the batch against the group's bounding box
+        int cls = 0, child0 = 0, nchild = 0, first = 0, count = 0;
+        double c[DIM], e2 = 0.0, mass = 0.0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) c[d] = 0.0;
+        if (node >= 0) {
+            c[0] = q0.x;
+            if (DIM >= 2) c[DIM >= 2 ? 1 : 0] = q0.y;
+            if (DIM >= 3) c[DIM >= 3 ? 2 : 0] = q1.x;
+            mass = q1.y;
+            e2 = q2.x;
+            child0 = __double2loint(q2.y); nchild = __double2hiint(q2.y);
+            double dmin2 = 0.0, dmax2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                const double slack = 1e-13 * (cmax + fabs(c[d])) + 1e-300;
+                double dc = bc[d] - c[d];
+                if (P.periodic) dc = min_image(dc, P.range[d]);
+                dc = fabs(dc);
+                const double lo = fmax(dc - bh[d] - slack, 0.0), hi = dc + bh[d] + slack;
+                dmin2 += lo * lo;
+                dmax2 += hi * hi;
+            }
+            if (e2 <= P.theta2 * dmin2 * (1.0 - 1e-9)) cls = 1;               // every lane accepts
+            else if (e2 > P.theta2 * dmax2 * (1.0 + 1e-9)) cls = 2;           // every lane opens
+            else cls = 3;
+            if (nchild == 0 && cls != 1) {
+                const double2 q3 = __ldg(t.ng + (size_t)node * 4 + 3);
+                first = __double2loint(q3.x); count = __double2hiint(q3.x);
+            }
+        }
+        if (cnt) {
+            for (int s = 0; s < k; ++s) n_visit += (__shfl_sync(SPHB_FULL_MASK, mask, s) >> lane) & 1u;
+        }
+        const unsigned b_acc = __ballot_sync(SPHB_FULL_MASK, cls == 1);
+        const unsigned b_mix = __ballot_sync(SPHB_FULL_MASK, cls == 3);
+        const unsigned b_oleaf = __ballot_sync(SPHB_FULL_MASK, cls == 2 && nchild == 0);
+        const unsigned b_oint = __ballot_sync(SPHB_FULL_MASK, cls == 2 && nchild > 0);
+
+        // (a) opened by every lane of the mask, internal: push the children with the same mask
+        if (b_oint) {
+            const int total = __popc(b_oint);
+            if (top + total > GV_STACK) {
+                if (lane == 0) atomicOr(&d_err[2], (unsigned long long)WALK_ERR_GRAV_STACK);
+            } else {
+                if ((b_oint >> lane) & 1u)
+                    sm.stack[top + __popc(b_oint & lt_mask)] = make_int2(child0 | ((nchild - 1) << 29), (int)mask);
+                top += total;
+            }
+        }
+        // (d) mixed nodes -> list in shared memory (tested lane by lane below)
+        const int nmix = __popc(b_mix);
+        if (cls == 3) {
+            const int slot = __popc(b_mix & lt_mask);
+            sm.mx[slot] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, mass);
+            sm.me2[slot] = e2;
+            sm.minfo[slot] = make_int4(child0, nchild, first, count);
+            sm.mmask[slot] = mask;
+        }
+        // (c) accepted by every lane of the mask -> chunk
+        {
+            unsigned ba = b_acc;
+            while (ba) {
+                const int take = min(32 - npc, __popc(ba));
+                const int rank = __popc(ba & lt_mask);
+                if (((ba >> lane) & 1u) && rank < take)
+                    sm.pc[npc + rank] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, mass);
+                for (int r = 0; r < take; ++r) {
+                    const int src = __ffs(ba) - 1;
+                    ba &= ba - 1;
+                    const unsigned m = __shfl_sync(SPHB_FULL_MASK, mask, src);
+                    if ((m >> lane) & 1u) pc_mask |= 1u << (npc + r);
+                }
+                npc += take;
+                if (npc == 32) flush_pc();
+            }
+        }
+        // (b) opened by every lane of the mask, leaf -> per-lane queues
+        {
+            unsigned bl = b_oleaf;
+            while (bl) {
+                const int src = __ffs(bl) - 1;
+                bl &= bl - 1;
+                const int f0 = __shfl_sync(SPHB_FULL_MASK, first, src);
+                const int c0 = __shfl_sync(SPHB_FULL_MASK, count, src);
+                const unsigned m = __shfl_sync(SPHB_FULL_MASK, mask, src);
+                queue_leaf((m >> lane) & 1u, f0, c0);
+            }
+        }
+        // ---- fetch the next batch now: its loads are in flight during the per-lane tests
+        __syncwarp();
+        pop_load();
+        // (e) mixed nodes: the reference's own per-particle test (src/bhtree.cpp:303-308)
+        for (int q = 0; q < nmix; ++q) {
+            const double4 c4 = sm.mx[q];
+            const double me2 = sm.me2[q];
+            const int4 info = sm.minfo[q];
+            const unsigned mm = sm.mmask[q];
+            bool open = false, accept = false;
+            if ((mm >> lane) & 1u) {
+                double cc[DIM], d[DIM];
+                vec_from4<DIM>(c4, cc);
+                calc_r_ij<DIM>(P, ri, cc, d);
+                const double d2 = abs2_exact<DIM>(d);
+                if (me2 > __dmul_rn(P.theta2, d2)) open = true;
+                else accept = true;
+            }
+            const unsigned a_b = __ballot_sync(SPHB_FULL_MASK, accept);
+            const unsigned o_b = __ballot_sync(SPHB_FULL_MASK, open);
+            if (a_b) {
+                if (accept) pc_mask |= 1u << npc;
+                if (lane == 0) sm.pc[npc] = c4;
+                if (++npc == 32) flush_pc();
+            }
+            if (o_b) {
+                if (info.y == 0) {
+                    queue_leaf(open, info.z, info.w);
+                } else if (top + 1 > GV_STACK) {
+                    if (lane == 0) atomicOr(&d_err[2], (unsigned long long)WALK_ERR_GRAV_STACK);
+                } else {
+                    if (lane == 0) sm.stack[top] = make_int2(info.x | ((info.y - 1) << 29), (int)o_b);
+                    top += 1;
                 }
             }
-            idx += 1;
-        } else {
-            idx += nd.skip;
         }
+        __syncwarp();
     }
     flush_pc();
     flush_pp();
@@ -848,11 +1090,12 @@ k_gravity(PSoA p, TreeDev t, DevParams P, int n, int i_begin, int i_end, const d
 #pragma unroll
         for (int a = 0; a < DIM; ++a) p.acc[a][i] = acc[a];
         p.phi[i] = phi;
+        tot_pp += n_pp; tot_pc += n_pc; tot_visit += n_visit;
+    }
+    __syncwarp();
     }
     if (cnt) {
-        const unsigned long long a = warp_sum_u64(valid ? (unsigned long long)n_pp : 0ull),
-                                 b = warp_sum_u64(valid ? (unsigned long long)n_pc : 0ull),
-                                 cc = warp_sum_u64(valid ? (unsigned long long)n_visit : 0ull);
+        const unsigned long long a = warp_sum_u64(tot_pp), b = warp_sum_u64(tot_pc), cc = warp_sum_u64(tot_visit);
         if (lane == 0) { atomicAdd(&cnt->grav_pp, a); atomicAdd(&cnt->grav_pc, b); atomicAdd(&cnt->grav_node_visits, cc); }
     }
 }
@@ -1014,60 +1257,56 @@ __global__ void k_energy(PSoA p, int n, double * __restrict__ out)
 template <int DIM>
 struct ListV {
     const DevParams & P; const PSoA & p;
-    double ri[DIM], h_i, h_i2;
+    double ri[DIM], h_i2;
     bool symmetric, fill;
     int cnt;
     int * out;           // fill: write p.orig[j] at out[cnt]
     long long cap_left;
-    __device__ __forceinline__ bool open(const NodeRec & nd)
+    __device__ __forceinline__ void hit(int j, const double4 & pj, double hj)
     {
-        const double h = symmetric ? fmax(h_i, nd.e) : h_i;
-        return node_in_reach<DIM>(P, nd, ri, h);
-    }
-    __device__ __forceinline__ void leaf(const NodeRec &, int base, int m, const double4 * sl)
-    {
-        for (int k = 0; k < m; ++k) {
-            const int j = base + k;
-            double d[DIM];
-            rij_from4<DIM>(P, ri, sl[k], d);
-            const double r2 = abs2_exact<DIM>(d);
-            double k2 = h_i2;
-            if (symmetric) { const double hj = p.sml[j]; k2 = fmax(h_i2, __dmul_rn(hj, hj)); }   // exhaustive_search.cpp:28
-            if (r2 < k2) {
-                if (fill && cnt < cap_left) out[cnt] = p.orig[j];
-                ++cnt;
-            }
+        double d[DIM];
+        rij_from4<DIM>(P, ri, pj, d);
+        const double r2 = abs2_exact<DIM>(d);
+        double k2 = h_i2;
+        if (symmetric) k2 = fmax(h_i2, __dmul_rn(hj, hj));     // exhaustive_search.cpp:28
+        if (r2 < k2) {
+            if (fill && cnt < cap_left) out[cnt] = p.orig[j];
+            ++cnt;
         }
     }
 };
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_neighbor_lists(PSoA p, TreeDev t, DevParams P, int n, const double * __restrict__ h_override /* sorted order or null */,
+k_neighbor_lists(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt, const double * __restrict__ h_override /* sorted order or null */,
                  int symmetric, int fill, int * __restrict__ counts, const long long * __restrict__ offsets,
-                 int * __restrict__ ids, long long cap_total, const double4 * __restrict__ posm)
+                 int * __restrict__ ids, long long cap_total, unsigned long long * __restrict__ d_err)
 {
-    __shared__ double4 s_leaf[4][32];
+    __shared__ NWalkSmem s_walk[4];
     const int lane = threadIdx.x & 31;
-    const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
-    const bool valid = i < n;
+    int g_first, g_cnt;
+    while (next_group(gt, lane, g_first, g_cnt)) {
+    const int i = g_first + lane;
+    const bool valid = lane < g_cnt;
     ListV<DIM> v{P, p};
     v.symmetric = symmetric != 0; v.fill = fill != 0; v.cnt = 0; v.out = nullptr; v.cap_left = 0;
-    v.h_i = 1.0;
+    double h_i = 1.0;
 #pragma unroll
     for (int a = 0; a < DIM; ++a) v.ri[a] = 0.0;
     if (valid) {
         load_vec<DIM>(p.pos, i, v.ri);
-        v.h_i = h_override ? h_override[i] : p.sml[i];
+        h_i = h_override ? h_override[i] : p.sml[i];
         if (fill) {
             const long long o = offsets[i];
             v.out = ids + (o < cap_total ? o : 0);
             v.cap_left = o < cap_total ? cap_total - o : 0;
         }
     }
-    v.h_i2 = __dmul_rn(v.h_i, v.h_i);
-    warp_walk<false>(t, posm, s_leaf[threadIdx.x >> 5], lane, v, valid);
+    v.h_i2 = __dmul_rn(h_i, h_i);
+    if (symmetric) group_stream<DIM, true>(t, P, rc.posm, p.sml, 1, s_walk[threadIdx.x >> 5], lane, v.ri, h_i, valid, v, d_err);
+    else group_stream<DIM, false>(t, P, rc.posm, nullptr, 0, s_walk[threadIdx.x >> 5], lane, v.ri, h_i, valid, v, d_err);
     if (valid && !fill) counts[i] = v.cnt;
+    }
 }
 
 // FP64 FMA micro-benchmark (roofline denominator)

@@ -10,12 +10,9 @@
 //   3. nodes are emitted level by level from the sorted keys with the reference's split rule
 //      (`num > leaf_particle_num && parent.level < max_level`, src/bhtree.cpp:154-158; the
 //      root always splits), children in child-index order;
-//   4. mass / mass centre / subtree size go bottom-up, and the nodes are laid out in DFS
-//      pre-order with a skip count per node, which makes every tree walk stackless.
-// Walks are warp-synchronous: a warp of 32 Morton-consecutive particles traverses the union of
-// its lanes' reference walks; each lane applies the reference's per-particle criterion itself
-// (so the set of nodes it opens / accepts is exactly the reference's) and sits out the subtrees
-// it did not open.  Node and leaf-particle loads are warp-uniform (one broadcast transaction).
+//   4. mass / mass centre go bottom-up; the nodes stay in this breadth-first order, in which the
+//      children of a node are contiguous (child0 .. child0 + nchild - 1), so that a walk can
+//      expand 32 nodes at a time with one lane per node (sphb_walk.cuh).
 #pragma once
 #include "sphb_math.cuh"
 #include <limits.h>
@@ -35,34 +32,24 @@ constexpr int PSOA_NDOUBLE = 12 + 12;   // permuted double arrays (without gradi
 
 // Nodes under construction (BFS order).
 struct TreeBuild {
-    int *first, *count, *level, *parent, *child0, *nchild, *size, *dfs;
+    int *first, *count, *level, *parent, *child0, *nchild;
     double *center[3];
     double *msum, *mpos[3];
 };
 
-// Finished tree, DFS pre-order, one packed 64-byte record (4 x double2) per node and walk kind so
-// that a node visit is four 16-byte warp-uniform loads off one address:
-//   nn (neighbour walks): [0] cx, cy   [1] cz, edge   [2] ksize, {skip, first}   [3] {count, leaf}, -
-//   ng (gravity walk):    [0] mx, my   [1] mz, mass   [2] edge^2, {skip, first}  [3] {count, leaf}, -
+// Finished tree, breadth-first order, one packed 64-byte record (4 x double2) per node and walk
+// kind, so that a lane fetches "its" node with four 16-byte loads off one address:
+//   nn (neighbour walks): [0] cx, cy   [1] cz, edge   [2] ksize,  {child0, nchild}   [3] {first, count}, -
+//   ng (gravity walk):    [0] mx, my   [1] mz, mass   [2] edge^2, {child0, nchild}   [3] {first, count}, -
 // (c = geometric centre, m = mass centre, ksize = BHNode::kernel_size set by set_kernel,
-//  skip = nodes in the subtree incl. this one, first/count = particle range, leaf = is_leaf)
+//  child0/nchild = contiguous children (nchild == 0: leaf), first/count = particle range)
 struct TreeDev {
     int      n_nodes;
     double2 *nn;
     double2 *ng;
-    int     *parent;    // DFS index of the parent, -1 for the root
+    int     *parent;    // index of the parent, -1 for the root
 };
-struct NodeRec { double x, y, z, w, e; int skip, first, count, leaf; };
-__device__ __forceinline__ NodeRec load_node(const double2 * __restrict__ base, int idx)
-{
-    const double2 * q = base + (size_t)idx * 4;
-    const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
-    NodeRec r;
-    r.x = q0.x; r.y = q0.y; r.z = q1.x; r.w = q1.y; r.e = q2.x;
-    r.skip = __double2loint(q2.y); r.first = __double2hiint(q2.y);
-    r.count = __double2loint(q3.x); r.leaf = __double2hiint(q3.x);
-    return r;
-}
+__device__ __forceinline__ double pack_ints(int lo, int hi) { return __hiloint2double(hi, lo); }
 __device__ __forceinline__ double * node_ksize(const TreeDev & t, int idx) { return &t.nn[(size_t)idx * 4 + 2].x; }
 
 // root[0..2] = centre, root[3] = edge.
@@ -255,7 +242,7 @@ __global__ void k_root_init(TreeBuild t, int n, const double * __restrict__ root
     }
 }
 
-// mass, sum m*pos, subtree size; one level per launch, deepest level first
+// mass, sum m*pos; one level per launch, deepest level first
 // (BHNode::assign accumulations, src/bhtree.cpp:199-201)
 template <int DIM>
 __global__ void k_level_up(TreeBuild t, PSoA p, int lvl_begin, int lvl_end)
@@ -265,7 +252,6 @@ __global__ void k_level_up(TreeBuild t, PSoA p, int lvl_begin, int lvl_end)
     double m = 0.0, mp[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) mp[d] = 0.0;
-    int size = 1;
     const int nc = t.nchild[i];
     if (nc == 0) {
         const int first = t.first[i], last = first + t.count[i];
@@ -281,26 +267,11 @@ __global__ void k_level_up(TreeBuild t, PSoA p, int lvl_begin, int lvl_end)
             m += t.msum[c0 + k];
 #pragma unroll
             for (int d = 0; d < DIM; ++d) mp[d] += t.mpos[d][c0 + k];
-            size += t.size[c0 + k];
         }
     }
     t.msum[i] = m;
 #pragma unroll
     for (int d = 0; d < DIM; ++d) t.mpos[d][i] = mp[d];
-    t.size[i] = size;
-}
-
-// DFS pre-order index of the children of every node of one level (top-down).
-__global__ void k_level_dfs(TreeBuild t, int lvl_begin, int lvl_end)
-{
-    const int i = lvl_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= lvl_end) return;
-    if (i == 0) t.dfs[0] = 0;
-    const int nc = t.nchild[i];
-    if (nc == 0) return;
-    const int c0 = t.child0[i];
-    int d = t.dfs[i] + 1;
-    for (int k = 0; k < nc; ++k) { t.dfs[c0 + k] = d; d += t.size[c0 + k]; }
 }
 
 template <int DIM>
@@ -308,7 +279,6 @@ __global__ void k_tree_scatter(TreeBuild t, TreeDev o, int n_nodes, const double
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
-    const int D = t.dfs[i];
     const int level = t.level[i];
     double c[3] = {0.0, 0.0, 0.0}, mc[3] = {0.0, 0.0, 0.0};
     double m = 0.0;
@@ -322,27 +292,67 @@ __global__ void k_tree_scatter(TreeBuild t, TreeDev o, int n_nodes, const double
         for (int d = 0; d < DIM; ++d) mc[d] = t.mpos[d][i] / m;       // src/bhtree.cpp:152
     }
     const double edge = ldexp(root[3], -(level - 1));
-    const double sf = __hiloint2double(t.first[i], t.size[i]);                 // {skip, first}
-    const double cl = __hiloint2double(t.nchild[i] == 0 ? 1 : 0, t.count[i]);  // {count, leaf}
-    double2 * nn = o.nn + (size_t)D * 4;
+    const int nc = t.nchild[i];
+    const double ch = pack_ints(nc ? t.child0[i] : 0, nc);            // {child0, nchild}
+    const double fc = pack_ints(t.first[i], t.count[i]);              // {first, count}
+    double2 * nn = o.nn + (size_t)i * 4;
     nn[0] = make_double2(c[0], c[1]); nn[1] = make_double2(c[2], edge);
-    nn[2] = make_double2(0.0, sf);    nn[3] = make_double2(cl, 0.0);
-    double2 * ng = o.ng + (size_t)D * 4;
+    nn[2] = make_double2(0.0, ch);    nn[3] = make_double2(fc, 0.0);
+    double2 * ng = o.ng + (size_t)i * 4;
     ng[0] = make_double2(mc[0], mc[1]); ng[1] = make_double2(mc[2], m);
-    ng[2] = make_double2(__dmul_rn(edge, edge), sf); ng[3] = make_double2(cl, 0.0);
-    o.parent[D] = (i == 0) ? -1 : t.dfs[t.parent[i]];
+    ng[2] = make_double2(__dmul_rn(edge, edge), ch); ng[3] = make_double2(fc, 0.0);
+    o.parent[i] = t.parent[i];
 }
 
-// packed {x, y, z, m} gather records of the particles (tree order), rebuilt by every make_tree
-template <int DIM>
-__global__ void k_pack_posm(PSoA p, double4 * __restrict__ posm, int n)
+// ---- particle groups ------------------------------------------------------------------------------
+// A group is the unit of work of every walk kernel: <= 32 consecutive particles of the tree order, one
+// per lane.  Plain 32-particle slices of the sorted order would now and then straddle the boundary of
+// two large cells (consecutive in the key order, far apart in space) and get a huge bounding box, so
+// groups are cut at the boundaries of "group cells": the tree nodes with <= GROUP_CELL_MAX particles
+// whose parent has more (and leaves above that size at the maximum level).  A group cell is chopped
+// into slices of 32; every group therefore lies inside one cube holding <= GROUP_CELL_MAX particles.
+constexpr int GROUP_CELL_MAX = 128;
+
+__global__ void k_group_flags(TreeBuild t, int n_nodes, unsigned char * __restrict__ flags, int slice_len, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double x = p.pos[0][i];
-    const double y = DIM >= 2 ? p.pos[DIM >= 2 ? 1 : 0][i] : 0.0;
-    const double z = DIM >= 3 ? p.pos[DIM >= 3 ? 2 : 0][i] : 0.0;
-    posm[i] = make_double4(x, y, z, p.mass[i]);
+    if (i >= n_nodes) return;
+    const int cnt = t.count[i];
+    const bool small = cnt <= GROUP_CELL_MAX;
+    const bool parent_big = (i == 0) || t.count[t.parent[i]] > GROUP_CELL_MAX;
+    if (!((small && parent_big) || (!small && t.nchild[i] == 0))) return;
+    const int first = t.first[i];
+    for (int k = 0; k < cnt; k += 32) flags[first + k] = 1;
+    // multi-GPU: a rank owns the particles [r * slice_len, (r + 1) * slice_len): groups end there too
+    if (slice_len > 0) {
+        const int r0 = (first + slice_len - 1) / slice_len;
+        for (int b = r0 * slice_len; b < first + cnt && b < n; b += slice_len) flags[b] = 1;
+    }
+}
+
+// ctl[0] = next group (work counter), ctl[1] = end group, for the particle range [p_begin, p_end)
+__global__ void k_group_range(const int * __restrict__ gstart, const int * __restrict__ n_groups, int p_begin, int p_end, int * __restrict__ ctl)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int ng = *n_groups;
+    auto lower = [&](int v) { int lo = 0, hi = ng; while (lo < hi) { const int mid = (lo + hi) >> 1; if (gstart[mid] < v) lo = mid + 1; else hi = mid; } return lo; };
+    ctl[0] = lower(p_begin);
+    ctl[1] = lower(p_end);
+}
+
+struct GroupTable { const int * start; const int * n_groups; int * ctl; int n; };
+
+// next group of this warp: particles [first, first + cnt); false when the range is exhausted
+__device__ __forceinline__ bool next_group(const GroupTable & gt, int lane, int & first, int & cnt)
+{
+    int g = 0;
+    if (lane == 0) g = atomicAdd(&gt.ctl[0], 1);
+    g = __shfl_sync(SPHB_FULL_MASK, g, 0);
+    if (g >= gt.ctl[1]) return false;
+    first = gt.start[g];
+    const int next = (g + 1 < *gt.n_groups) ? gt.start[g + 1] : gt.n;
+    cnt = next - first;
+    return true;
 }
 
 // BHNode::set_kernel (src/bhtree.cpp:206-232): per node the largest sml beneath it.
@@ -356,8 +366,8 @@ __global__ void k_set_kernel(TreeDev t, const double * __restrict__ sml)
     const int D = blockIdx.x * blockDim.x + threadIdx.x;
     if (D >= t.n_nodes) return;
     const double2 q2 = t.nn[(size_t)D * 4 + 2], q3 = t.nn[(size_t)D * 4 + 3];
-    if (!__double2hiint(q3.x)) return;
-    const int first = __double2hiint(q2.y), count = __double2loint(q3.x);
+    if (__double2hiint(q2.y)) return;                  // internal node
+    const int first = __double2loint(q3.x), count = __double2hiint(q3.x);
     double h = 0.0;
     for (int j = first; j < first + count; ++j) { const double s = sml[j]; if (s > h) h = s; }
     const unsigned long long hb = (unsigned long long)__double_as_longlong(h);
@@ -367,78 +377,6 @@ __global__ void k_set_kernel(TreeDev t, const double * __restrict__ sml)
         if (old >= hb) break;          // whoever wrote `old` carries it (or more) upward
         q = t.parent[q];
     }
-}
-
-// ---- the stackless warp walk ----------------------------------------------------------------------
-// A warp of 32 consecutive particles visits the union of its lanes' reference walks.
-// V provides   bool open(const NodeRec &)                          the lane's own criterion
-//              void leaf(const NodeRec &, int base, int m, const double4 * s)
-//                   the lane opened this leaf; s[0..m) = {x,y,z,m} of particles base .. base+m-1,
-//                   staged in shared memory by one coalesced load of the whole warp.
-// PREFETCH: fetch both possible successors before the (dependent) test of the current node.  It takes
-// the uniform-load latency off the critical path at the price of ~30 registers; measured on B200 it
-// pays for the pre-interaction walks and costs occupancy in the force / gravity walks.
-template <bool PREFETCH, class V>
-__device__ __forceinline__ void warp_walk(const TreeDev & t, const double4 * __restrict__ posm, double4 * s_leaf,
-                                          int lane, V & v, bool lane_valid)
-{
-    int idx = 0;
-    int resume = lane_valid ? 0 : INT_MAX;       // lane takes part iff idx >= resume
-    const int n_nodes = t.n_nodes;
-    NodeRec nd;
-    if (PREFETCH) nd = load_node(t.nn, 0);
-    while (idx < n_nodes) {
-        NodeRec n_down, n_skip;
-        if (!PREFETCH) nd = load_node(t.nn, idx);
-        if (PREFETCH) {
-            n_down = load_node(t.nn, min(idx + 1, n_nodes - 1));
-            n_skip = load_node(t.nn, min(idx + nd.skip, n_nodes - 1));
-        }
-        bool open = false;
-        if (idx >= resume) {
-            open = v.open(nd);
-            if (!open) resume = idx + nd.skip;
-        }
-        if (__any_sync(SPHB_FULL_MASK, open)) {
-            if (nd.leaf) {
-                const int last = nd.first + nd.count;
-                for (int base = nd.first; base < last; base += 32) {
-                    const int m = min(32, last - base);
-                    __syncwarp();
-                    if (lane < m) s_leaf[lane] = ldg4(&posm[base + lane]);
-                    __syncwarp();
-                    if (open) v.leaf(nd, base, m, s_leaf);
-                }
-            }
-            idx += 1;
-            if (PREFETCH) nd = n_down;
-        } else {
-            idx += nd.skip;
-            if (PREFETCH) nd = n_skip;
-        }
-    }
-    __syncwarp();
-}
-
-// Per-lane neighbour criterion of BHNode::neighbor_search (src/bhtree.cpp:236-249):
-// Chebyshev minimum-image distance to the geometric centre <= edge/2 + h.
-template <int DIM>
-__device__ __forceinline__ bool node_in_reach(const DevParams & P, const NodeRec & g, const double (&ri)[DIM], double h)
-{
-    const double l2 = (g.w * 0.5 + h) * (g.w * 0.5 + h);
-    double c[DIM];
-    c[0] = g.x;
-    if (DIM >= 2) c[DIM >= 2 ? 1 : 0] = g.y;
-    if (DIM >= 3) c[DIM >= 3 ? 2 : 0] = g.z;
-    double d[DIM];
-    calc_r_ij<DIM>(P, ri, c, d);
-    double dx2_max = d[0] * d[0];
-#pragma unroll
-    for (int k = 1; k < DIM; ++k) {
-        const double dx2 = d[k] * d[k];
-        if (dx2 > dx2_max) dx2_max = dx2;
-    }
-    return dx2_max <= l2;
 }
 
 // r_ij = r_i - {x,y,z of a staged particle}, minimum image if periodic

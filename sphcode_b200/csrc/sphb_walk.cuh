@@ -1,0 +1,263 @@
+// sphb_walk.cuh — group neighbour search: replaces BHTree::neighbor_search (src/bhtree.cpp:114-126,
+// 234-270) and exhaustive_search (src/exhaustive_search.cpp:11-42) for a whole warp at once.
+//
+// A group = 32 consecutive particles of the tree order = one warp, lane = particle i.
+//   1. Tree descent, breadth-first with ONE LANE PER NODE: up to 32 nodes are popped from a
+//      shared-memory stack, every lane fetches its node's 64-byte record and tests the node's cube
+//      against the group's bounding box grown by the search radius (for the symmetric search: by
+//      max(radius, BHNode::kernel_size of the node), src/bhtree.cpp:237).  Children of hit nodes are
+//      pushed, hit leaves are streamed.  No per-particle pointer chasing, 32 node loads in flight.
+//   2. Candidate streaming: the particles of the hit leaves are staged 32 at a time into a
+//      shared-memory tile ({x,y,z,m} FP64 + a group-relative FP32 copy); every lane runs the SAME
+//      loop over the tile (convergent, broadcast reads) with a conservative FP32 distance test that
+//      only produces a hit mask; the FP32 pipe is otherwise idle in this code and runs at twice the
+//      FP64 rate.
+//   3. Each lane passes its (few) hits to the visitor, which applies the reference's exact FP64
+//      predicate (r2 < h2 with the reference's operation order) — so the neighbour SET is exactly
+//      the reference's; the tree and the FP32 test only ever discard pairs that cannot pass.
+// The cull is conservative by construction (margins below), hence the set equals the
+// EXHAUSTIVE_SEARCH set, which the reference's tree search reproduces as well.
+#pragma once
+#include "sphb_tree.cuh"
+
+namespace sphb {
+
+constexpr int NW_STACK = 512;      // node stack entries per warp
+
+struct NWalkSmem {
+    int     stack[NW_STACK];       // child0 | (nchild - 1) << 29: all children of a hit node
+    int     expand[32];            // nodes of the batch being fetched
+    double4 tile64[32];            // {x, y, z, m} of the staged candidates
+    float4  tile32[32];            // {x - ref, y - ref, z - ref, symmetric threshold} in FP32
+    double  tileh[32];             // h_j (symmetric search only)
+    int     tilej[32];             // particle index
+};
+
+// error bits reported through d_err[2]
+enum { WALK_ERR_STACK = 1, WALK_ERR_GRAV_STACK = 2 };
+
+// Bounding box of the group's valid lanes: centre and half width per axis (warp-uniform).
+template <int DIM>
+__device__ __forceinline__ void group_box(const double (&ri)[DIM], bool valid, double (&bc)[DIM], double (&bh)[DIM])
+{
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        const double lo = warp_min(valid ? ri[d] : 1.7976931348623157e308);
+        const double hi = warp_max(valid ? ri[d] : -1.7976931348623157e308);
+        bc[d] = 0.5 * lo + 0.5 * hi;
+        bh[d] = fmax(hi - bc[d], bc[d] - lo) * (1.0 + 1e-12);
+    }
+}
+
+// Per-lane state of the FP32 pre-filter.
+template <int DIM> struct Filter32 {
+    float fi[DIM];        // x_i - ref
+    float thr;            // squared threshold of lane i (negative: lane inactive)
+    float L[DIM];         // periodic range (FP32), only if periodic
+    double ref[DIM];      // = group box centre
+    double rlim;          // candidates farther than this from ref (max norm) cannot be gather neighbours
+    double delta;         // absolute per-axis error bound of the FP32 coordinates inside rlim
+};
+
+// V:  void hit(int j, const double4 & pj, double hj)   — lane's conservative hit; exact test inside.
+// reach = search radius of the group (max over lanes), h_i = lane's own radius (gather: h_search,
+// symmetric: sml_i).  hj_src / hj_stride: where h_j lives for the symmetric search.
+template <int DIM, bool SYM, class V>
+__device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams & P, const double4 * __restrict__ posm,
+                                             const double * __restrict__ hj_src, int hj_stride,
+                                             NWalkSmem & sm, int lane, const double (&ri)[DIM], double h_i, bool valid,
+                                             V & v, unsigned long long * __restrict__ d_err)
+{
+    double bc[DIM], bh[DIM];
+    group_box<DIM>(ri, valid, bc, bh);
+    const double reach = warp_max(valid ? h_i : 0.0);
+    double bhmax = bh[0];
+#pragma unroll
+    for (int d = 1; d < DIM; ++d) bhmax = fmax(bhmax, bh[d]);
+    // slack for the rounding of node centres / box arithmetic (coordinates are O(root edge))
+    double cmax = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) cmax = fmax(cmax, fabs(bc[d]) + bh[d]);
+    const double slack = 1e-13 * (cmax + reach) + 1e-300;
+
+    // ---- FP32 filter set-up
+    Filter32<DIM> F;
+    double lmax = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        F.ref[d] = bc[d];
+        F.fi[d] = (float)(ri[d] - bc[d]);
+        F.L[d] = (float)P.range[d];
+        if (P.periodic) lmax = fmax(lmax, P.range[d]);
+    }
+    F.rlim = (bhmax + reach) * 1.001 + slack;
+    F.delta = 1.1920929e-7 * (F.rlim + lmax);            // 2^-23 * magnitude bound
+    {
+        const double hh = h_i + 4.0 * F.delta;
+        F.thr = valid ? (float)(hh * hh * (1.0 + 4e-6)) : -1.0f;
+    }
+
+    int fill = 0;                                        // staged candidates in the current tile
+
+    auto process = [&](int m) {
+        unsigned hits = 0;
+        if (P.periodic) {
+#pragma unroll 8
+            for (int k = 0; k < m; ++k) {
+                const float4 c = sm.tile32[k];
+                float ax = fabsf(F.fi[0] - c.x);
+                ax = fminf(ax, F.L[0] - ax);
+                float r2 = ax * ax;
+                if (DIM >= 2) { float ay = fabsf(F.fi[DIM >= 2 ? 1 : 0] - c.y); ay = fminf(ay, F.L[DIM >= 2 ? 1 : 0] - ay); r2 = fmaf(ay, ay, r2); }
+                if (DIM >= 3) { float az = fabsf(F.fi[DIM >= 3 ? 2 : 0] - c.z); az = fminf(az, F.L[DIM >= 3 ? 2 : 0] - az); r2 = fmaf(az, az, r2); }
+                const float th = SYM ? fmaxf(F.thr, c.w) : F.thr;
+                if (r2 < th) hits |= 1u << k;
+            }
+        } else {
+#pragma unroll 8
+            for (int k = 0; k < m; ++k) {
+                const float4 c = sm.tile32[k];
+                const float dx = F.fi[0] - c.x;
+                float r2 = dx * dx;
+                if (DIM >= 2) { const float dy = F.fi[DIM >= 2 ? 1 : 0] - c.y; r2 = fmaf(dy, dy, r2); }
+                if (DIM >= 3) { const float dz = F.fi[DIM >= 3 ? 2 : 0] - c.z; r2 = fmaf(dz, dz, r2); }
+                const float th = SYM ? fmaxf(F.thr, c.w) : F.thr;
+                if (r2 < th) hits |= 1u << k;
+            }
+        }
+        if (!valid) hits = 0;
+        while (hits) {
+            const int kb = __ffs(hits) - 1;
+            hits &= hits - 1;
+            v.hit(sm.tilej[kb], sm.tile64[kb], SYM ? sm.tileh[kb] : 0.0);
+        }
+    };
+
+    // stage particles [first, first + count) of a hit leaf, processing tiles as they fill up
+    auto feed = [&](int first, int count) {
+        int off = 0;
+        while (off < count) {
+            const int take = min(count - off, 32 - fill);
+            if (lane >= fill && lane < fill + take) {
+                const int j = first + off + (lane - fill);
+                const double4 pj = ldg4(&posm[j]);
+                double dj[DIM];
+                dj[0] = pj.x - F.ref[0];
+                if (DIM >= 2) dj[DIM >= 2 ? 1 : 0] = pj.y - F.ref[DIM >= 2 ? 1 : 0];
+                if (DIM >= 3) dj[DIM >= 3 ? 2 : 0] = pj.z - F.ref[DIM >= 3 ? 2 : 0];
+                double amax = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    if (P.periodic) dj[d] = min_image(dj[d], P.range[d]);
+                    amax = fmax(amax, fabs(dj[d]));
+                }
+                float4 f = make_float4((float)dj[0], DIM >= 2 ? (float)dj[DIM >= 2 ? 1 : 0] : 0.f,
+                                       DIM >= 3 ? (float)dj[DIM >= 3 ? 2 : 0] : 0.f, -1.0f);
+                if (SYM) {
+                    const double hj = __ldg(hj_src + (size_t)j * hj_stride);
+                    const double dl = 1.1920929e-7 * (fmax(amax, F.rlim) + lmax);
+                    const double hh = hj + 4.0 * (dl + F.delta);
+                    f.w = (float)(hh * hh * (1.0 + 4e-6));
+                    sm.tileh[lane] = hj;
+                } else if (amax > F.rlim) {
+                    f.x = 3e18f;                         // cannot be within h_search of any lane
+                }
+                sm.tile64[lane] = pj;
+                sm.tile32[lane] = f;
+                sm.tilej[lane] = j;
+            }
+            fill += take;
+            off += take;
+            if (fill == 32) {
+                __syncwarp();
+                process(32);
+                __syncwarp();
+                fill = 0;
+            }
+        }
+    };
+
+    // ---- breadth-first descent, one lane per node.  A stack entry stands for all (contiguous)
+    // children of a hit node: a batch of <= 32 nodes pushes <= 32 entries and pops >= 32 / 2^DIM.
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int top = 1;
+    if (lane == 0) sm.stack[0] = 0;                      // the root alone: child0 = 0, nchild = 1
+    __syncwarp();
+    while (top > 0) {
+        const int ne = min(top, 32);
+        int ent = 0, nc = 0;
+        if (lane < ne) { ent = sm.stack[top - 1 - lane]; nc = (int)((unsigned)ent >> 29) + 1; }
+        int incl = nc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(SPHB_FULL_MASK, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int m = __popc(__ballot_sync(SPHB_FULL_MASK, lane < ne && incl <= 32));   // entries taken (a prefix)
+        const int k = __shfl_sync(SPHB_FULL_MASK, incl, m - 1);
+        if (lane < m) {
+            const int c0 = ent & 0x1fffffff;
+            for (int ci = 0; ci < nc; ++ci) sm.expand[incl - nc + ci] = c0 + ci;
+        }
+        __syncwarp();
+        int node = -1;
+        if (lane < k) node = sm.expand[lane];
+        top -= m;
+        __syncwarp();
+        bool hit = false;
+        int child0 = 0, nchild = 0, first = 0, count = 0;
+        if (node >= 0) {
+            const double2 * q = t.nn + (size_t)node * 4;
+            const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            const double half = 0.5 * q1.y;
+            const double rn = SYM ? fmax(reach, q2.x) : reach;
+            double c[DIM];
+            c[0] = q0.x;
+            if (DIM >= 2) c[DIM >= 2 ? 1 : 0] = q0.y;
+            if (DIM >= 3) c[DIM >= 3 ? 2 : 0] = q1.x;
+            double g2 = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                double dc = bc[d] - c[d];
+                if (P.periodic) dc = min_image(dc, P.range[d]);
+                const double gap = fabs(dc) - (bh[d] + half) - slack;
+                if (gap > 0.0) g2 += gap * gap;
+            }
+            hit = g2 <= rn * rn * (1.0 + 1e-9);
+            if (hit) {
+                child0 = __double2loint(q2.y); nchild = __double2hiint(q2.y);
+                if (nchild == 0) {
+                    const double2 q3 = __ldg(q + 3);
+                    first = __double2loint(q3.x); count = __double2hiint(q3.x);
+                }
+            }
+        }
+        const bool is_leaf = hit && nchild == 0;
+        unsigned leaf_b = __ballot_sync(SPHB_FULL_MASK, is_leaf);
+        const unsigned int_b = __ballot_sync(SPHB_FULL_MASK, hit && nchild > 0);
+        if (int_b) {
+            const int total = __popc(int_b);
+            if (top + total > NW_STACK) {
+                if (lane == 0) atomicOr(&d_err[2], (unsigned long long)WALK_ERR_STACK);
+            } else {
+                if ((int_b >> lane) & 1u) sm.stack[top + __popc(int_b & lt_mask)] = child0 | ((nchild - 1) << 29);
+                top += total;
+            }
+            __syncwarp();
+        }
+        while (leaf_b) {
+            const int src = __ffs(leaf_b) - 1;
+            leaf_b &= leaf_b - 1;
+            const int f0 = __shfl_sync(SPHB_FULL_MASK, first, src);
+            const int c0 = __shfl_sync(SPHB_FULL_MASK, count, src);
+            feed(f0, c0);
+        }
+    }
+    if (fill > 0) {
+        __syncwarp();
+        process(fill);
+    }
+    __syncwarp();
+}
+
+} // namespace sphb
