@@ -559,7 +559,9 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
         k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, c->rc.hsoft, c->n); LAUNCH_CHECK();
         GroupTable gt;
         if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
-        k_gravity<DIM><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, c->counters_on ? c->d_cnt : nullptr, c->d_err);
+        static bool attr_set = false;
+        if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(GravSmem)))); attr_set = true; }
+        k_gravity<DIM><<<c->pre_grid, 128, 4 * sizeof(GravSmem), c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, c->counters_on ? c->d_cnt : nullptr, c->d_err);
         LAUNCH_CHECK();
     }
     return 0;

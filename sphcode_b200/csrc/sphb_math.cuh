@@ -186,6 +186,18 @@ __device__ __forceinline__ void soft_fg(double r, double rinv, double einv, doub
     }
 }
 
+// 1/sqrt(x) for normal x > 0: hardware seed (MUFU.RSQ64H, relative error < 2^-22) + one third-order
+// step  y (1 + e/2 + 3 e^2/8),  e = 1 - x y^2  (error ~ e^3: below 1 ulp).  No special cases:
+// x = 0 / inf / nan give nan — callers use it only on squared distances known to be positive.
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y * y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(y, e * p, y);
+}
+
 // read-only 32-byte load (no double4 overload of __ldg): two 16-byte non-coherent loads
 __device__ __forceinline__ double4 ldg4(const double4 * p)
 {

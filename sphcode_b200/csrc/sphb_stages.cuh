@@ -748,11 +748,12 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 //     read through L1; lanes of a warp are Morton neighbours and share these lines).
 constexpr int GRAV_LQ = 8;        // leaf queue depth per lane
 constexpr int GV_STACK = 704;     // node stack entries per warp (<= 28 stay behind per tree level, see pop_load)
+constexpr int GV_PC = 64;         // accepted cells per chunk
 
 struct GravSmem {
     int2     stack[GV_STACK];           // {child0 | (nchild - 1) << 29, lane mask}: the children of an opened node
     int2     expand[32];                // {node, lane mask} of the batch being fetched
-    double4  pc[32];                    // accepted cells of the current chunk
+    double   pcx[GV_PC], pcy[GV_PC], pcz[GV_PC], pcm[GV_PC];   // accepted cells of the current chunk: mass centre, G * mass
     double4  mx[32];                    // mixed nodes of the current batch: mass centre + mass
     double   me2[32];                   //   edge^2
     int4     minfo[32];                 //   {child0, nchild, first, count}
@@ -786,9 +787,9 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
           const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, Counters * __restrict__ cnt,
           unsigned long long * __restrict__ d_err)
 {
-    __shared__ GravSmem s_all[4];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    GravSmem & sm = s_all[w];
+    GravSmem & sm = reinterpret_cast<GravSmem *>(s_dyn)[w];
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long tot_pp = 0, tot_pc = 0, tot_visit = 0;
     int g_first, g_cnt;
@@ -804,37 +805,50 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         h_i = p.sml[i];
     }
     const double einv_i = 2.0 / h_i;
-    const double h_i2 = h_i * h_i;
+    const double h_i2 = h_i * h_i * (1.0 + 1e-12);   // near test: r2 < max(h_i, h_j)^2 with a margin
     unsigned int n_pp = 0, n_pc = 0, n_visit = 0;             // per lane: fit 32 bits
-    unsigned pc_mask = 0;
+    unsigned pc_lo = 0, pc_hi = 0;                           // lane's accept bits over the chunk (entries 0-31, 32-63)
     int npc = 0, nlq = 0;
 
     double bc[DIM], bh[DIM];
     group_box<DIM>(ri, valid, bc, bh);
     const unsigned vmask = __ballot_sync(SPHB_FULL_MASK, valid);
 
-    // accepted cells of the current chunk: monopole, src/bhtree.cpp:326-330
+    // accepted cells of the current chunk: monopole, src/bhtree.cpp:326-330; two cells in flight
     auto flush_pc = [&]() {
         __syncwarp();
-        unsigned mm = pc_mask;
-        while (mm) {
-            const int e = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const double4 c = sm.pc[e];
-            double d[DIM];
-            rij_from4<DIM>(P, ri, c, d);
-            const double d2 = dot<DIM>(d, d);
-            const double r_inv = rsqrt(d2);
-            const double gm = P.G * c.w;
-            phi -= gm * r_inv;
-            const double s = gm * (r_inv * r_inv * r_inv);
+        n_pc += __popc(pc_lo) + __popc(pc_hi);
 #pragma unroll
-            for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
-            ++n_pc;
+        for (int half = 0; half < 2; ++half) {
+            unsigned mm = half ? pc_hi : pc_lo;
+            const double * px = sm.pcx + half * 32, * py = sm.pcy + half * 32, * pz = sm.pcz + half * 32, * pm = sm.pcm + half * 32;
+            while (mm) {
+                const int e0 = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const bool two = mm != 0;
+                const int e1 = two ? __ffs(mm) - 1 : e0;
+                mm &= mm - 1;                                  // stays 0 when !two
+                double c0[DIM], c1[DIM], d0[DIM], d1[DIM];
+                c0[0] = px[e0]; c1[0] = px[e1];
+                if (DIM >= 2) { c0[DIM >= 2 ? 1 : 0] = py[e0]; c1[DIM >= 2 ? 1 : 0] = py[e1]; }
+                if (DIM >= 3) { c0[DIM >= 3 ? 2 : 0] = pz[e0]; c1[DIM >= 3 ? 2 : 0] = pz[e1]; }
+                const double gm0 = pm[e0], gm1 = two ? pm[e1] : 0.0;
+                calc_r_ij<DIM>(P, ri, c0, d0);
+                calc_r_ij<DIM>(P, ri, c1, d1);
+                const double ri0 = fast_rsqrt(dot<DIM>(d0, d0)), ri1 = fast_rsqrt(dot<DIM>(d1, d1));
+                phi -= gm0 * ri0;
+                phi -= gm1 * ri1;
+                const double s0 = gm0 * ri0 * (ri0 * ri0), s1 = gm1 * ri1 * (ri1 * ri1);
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
+            }
         }
-        pc_mask = 0;
+        pc_lo = pc_hi = 0;
         npc = 0;
         __syncwarp();
+    };
+    auto pc_set = [&](unsigned bit, int e) {                 // bit (0/1) of this lane for chunk entry e
+        if (e < 32) pc_lo |= bit << e; else pc_hi |= bit << (e - 32);
     };
     // queued leaves: particle-particle sums of src/bhtree.cpp:309-317.  Pass 1 runs one flattened
     // loop over all particles of the lane's queued leaves with the unsoftened form (u >= 2 for both
@@ -848,22 +862,23 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         while (q < nlq) {
             const int j = cur.x + k;
             const double4 pj = ldg4(&posm[j]);
-            const double hj2 = __ldg(&hsoft[j]).y;
+            const double hj2 = __ldg(&hsoft[j].y);         // h_j^2 (1 + 1e-12)
             double d[DIM];
             rij_from4<DIM>(P, ri, pj, d);
             const double r2 = dot<DIM>(d, d);
-            if (r2 < fmax(h_i2, hj2) * (1.0 + 1e-12)) {
-                near |= 1u << k;
-            } else {
-                const double rinv = rsqrt(r2);
-                const double gm = P.G * pj.w;
+            {
+                // branch-free: a softened ("near") pair contributes 0 here and is marked for pass 2
+                const bool nr = r2 < fmax(h_i2, hj2);
+                near |= (nr ? 1u : 0u) << k;
+                const double rinv = fast_rsqrt(nr ? 1.0 : r2);
+                const double gm = nr ? 0.0 : P.G * pj.w;
                 phi -= gm * rinv;
                 const double s = gm * (rinv * rinv * rinv);
 #pragma unroll
                 for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
             }
-            ++n_pp;
             if (++k == cur.y) {
+                n_pp += k;
                 sm.near[q][lane] = near;
                 near = 0;
                 k = 0;
@@ -1019,18 +1034,23 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         {
             unsigned ba = b_acc;
             while (ba) {
-                const int take = min(32 - npc, __popc(ba));
+                const int take = min(GV_PC - npc, __popc(ba));
                 const int rank = __popc(ba & lt_mask);
-                if (((ba >> lane) & 1u) && rank < take)
-                    sm.pc[npc + rank] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, mass);
+                if (((ba >> lane) & 1u) && rank < take) {
+                    const int e = npc + rank;
+                    sm.pcx[e] = c[0];
+                    if (DIM >= 2) sm.pcy[e] = c[DIM >= 2 ? 1 : 0];
+                    if (DIM >= 3) sm.pcz[e] = c[DIM >= 3 ? 2 : 0];
+                    sm.pcm[e] = P.G * mass;
+                }
                 for (int r = 0; r < take; ++r) {
                     const int src = __ffs(ba) - 1;
                     ba &= ba - 1;
                     const unsigned m = __shfl_sync(SPHB_FULL_MASK, mask, src);
-                    if ((m >> lane) & 1u) pc_mask |= 1u << (npc + r);
+                    pc_set((m >> lane) & 1u, npc + r);
                 }
                 npc += take;
-                if (npc == 32) flush_pc();
+                if (npc == GV_PC) flush_pc();
             }
         }
         // (b) opened by every lane of the mask, leaf -> per-lane queues
@@ -1066,9 +1086,14 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             const unsigned a_b = __ballot_sync(SPHB_FULL_MASK, accept);
             const unsigned o_b = __ballot_sync(SPHB_FULL_MASK, open);
             if (a_b) {
-                if (accept) pc_mask |= 1u << npc;
-                if (lane == 0) sm.pc[npc] = c4;
-                if (++npc == 32) flush_pc();
+                pc_set(accept ? 1u : 0u, npc);
+                if (lane == 0) {
+                    sm.pcx[npc] = c4.x;
+                    if (DIM >= 2) sm.pcy[npc] = c4.y;
+                    if (DIM >= 3) sm.pcz[npc] = c4.z;
+                    sm.pcm[npc] = P.G * c4.w;
+                }
+                if (++npc == GV_PC) flush_pc();
             }
             if (o_b) {
                 if (info.y == 0) {
@@ -1106,7 +1131,7 @@ __global__ void k_grav_pack(const double * __restrict__ sml, double2 * __restric
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double h = sml[i];
-    hsoft[i] = make_double2(2.0 / h, h * h);
+    hsoft[i] = make_double2(2.0 / h, h * h * (1.0 + 1e-12));
 }
 
 // Direct sum, the EXHAUSTIVE_SEARCH flavour of GravityForce (src/gravity_force.cpp:70-84).
