@@ -7,6 +7,7 @@
 #include "sphb_stages.cuh"
 
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <dlfcn.h>
 #include <algorithm>
 #include <cfloat>
@@ -96,6 +97,7 @@ struct sphb_ctx {
     int * grp_start = nullptr;             // first particle of every group, ascending
     int * d_ngroups = nullptr;             // number of groups (device)
     int * d_grp_ctl = nullptr;             // [0] work counter, [1] end group of the current kernel
+    int2 * grav_lq = nullptr; unsigned * grav_near = nullptr;   // per-warp leaf queues of the gravity walk
     Recs rc{};                             // packed gather records (tree order)
     bool recs_dirty = true;                // SoA fields changed since the records were packed
 
@@ -203,7 +205,7 @@ int alloc_particles(sphb_ctx * c, int n)
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int *)nullptr, (int *)nullptr, 5 * n + 2, c->stream);
     size_t sel_bytes = 0;
-    cub::DeviceSelect::Flagged(nullptr, sel_bytes, cub::CountingInputIterator<int>(0), (unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, n, c->stream);
+    cub::DeviceSelect::Flagged(nullptr, sel_bytes, thrust::counting_iterator<int>(0), (unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, n, c->stream);
     c->cub_tmp_bytes = std::max(std::max(c->cub_tmp_bytes, scan_bytes), sel_bytes) + 256;
     { char * t = nullptr; if (dev_alloc(c, &t, c->cub_tmp_bytes, c->allocs)) return 1; c->cub_tmp = t; }
     c->bbox_blocks = std::min(cdiv(n, 256), 4 * c->sm_count);
@@ -217,6 +219,9 @@ int alloc_particles(sphb_ctx * c, int n)
     if (c->P.sph_type != T_DISPH) { if (dev_alloc(c, &c->scratch_m, slots * c->P.list_cap * 32, c->allocs)) return 1; }
     else c->scratch_m = nullptr;
     if (dev_alloc(c, &c->grp_flags, np + 32, c->allocs) || dev_alloc(c, &c->grp_start, np + 32, c->allocs)) return 1;
+    if (c->P.use_gravity) {
+        if (dev_alloc(c, &c->grav_lq, slots * GRAV_LQ * 32, c->allocs) || dev_alloc(c, &c->grav_near, slots * GRAV_LQ * 32, c->allocs)) return 1;
+    }
     // packed gather records
     if (dev_alloc(c, &c->rc.posm, np, c->allocs) || dev_alloc(c, &c->rc.velc, np, c->allocs) ||
         dev_alloc(c, &c->rc.thermo, np, c->allocs) || dev_alloc(c, &c->rc.av, np, c->allocs) ||
@@ -418,7 +423,7 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     k_group_flags<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->world > 1 ? c->slice_groups * 32 : 0, n); LAUNCH_CHECK();
     {
         size_t tb = c->cub_tmp_bytes;
-        CK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, cub::CountingInputIterator<int>(0), c->grp_flags, c->grp_start, c->d_ngroups, n, c->stream));
+        CK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, thrust::counting_iterator<int>(0), c->grp_flags, c->grp_start, c->d_ngroups, n, c->stream));
         ++c->launches;
     }
     c->tree_valid = true;
@@ -561,7 +566,7 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
         if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
         static bool attr_set = false;
         if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(GravSmem)))); attr_set = true; }
-        k_gravity<DIM><<<c->pre_grid, 128, 4 * sizeof(GravSmem), c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, c->counters_on ? c->d_cnt : nullptr, c->d_err);
+        k_gravity<DIM><<<c->pre_grid, 128, 4 * sizeof(GravSmem), c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, c->grav_lq, c->grav_near, c->counters_on ? c->d_cnt : nullptr, c->d_err);
         LAUNCH_CHECK();
     }
     return 0;

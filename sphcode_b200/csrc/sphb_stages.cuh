@@ -746,7 +746,7 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 //   * opened leaves go to a per-lane queue of (first, count); when any lane's queue is full, every
 //     lane runs one flattened loop over all particles of its queued leaves (packed x,y,z,m + 2/h
 //     read through L1; lanes of a warp are Morton neighbours and share these lines).
-constexpr int GRAV_LQ = 8;        // leaf queue depth per lane
+constexpr int GRAV_LQ = 64;       // leaf queue depth per lane (global scratch, [entry][lane])
 constexpr int GV_STACK = 704;     // node stack entries per warp (<= 28 stay behind per tree level, see pop_load)
 constexpr int GV_PC = 64;         // accepted cells per chunk
 
@@ -758,8 +758,6 @@ struct GravSmem {
     double   me2[32];                   //   edge^2
     int4     minfo[32];                 //   {child0, nchild, first, count}
     unsigned mmask[32];                 //   lane mask
-    int2     lq[GRAV_LQ][32];           // per-lane queue of opened leaves
-    unsigned near[GRAV_LQ][32];         // softened pairs of a queued leaf
 };
 
 // Softening functions with the divisions by constants turned into products (soft_fg in
@@ -784,12 +782,16 @@ __device__ __forceinline__ void soft_fg_fast(double r, double rinv, double einv,
 template <int DIM>
 __global__ void __launch_bounds__(128, 4)
 k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restrict__ posm,
-          const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, Counters * __restrict__ cnt,
-          unsigned long long * __restrict__ d_err)
+          const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, int2 * __restrict__ scratch_lq,
+          unsigned * __restrict__ scratch_near, Counters * __restrict__ cnt, unsigned long long * __restrict__ d_err)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     GravSmem & sm = reinterpret_cast<GravSmem *>(s_dyn)[w];
+    // per-lane queue of opened leaves {first, count} and of their softened-pair masks: deep enough that
+    // the lanes' particle-particle work evens out before a flush; lives in this warp's scratch slot
+    int2 * const lq = scratch_lq + ((size_t)(blockIdx.x * (blockDim.x >> 5) + w) * GRAV_LQ) * 32 + lane;
+    unsigned * const nearq = scratch_near + ((size_t)(blockIdx.x * (blockDim.x >> 5) + w) * GRAV_LQ) * 32 + lane;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long tot_pp = 0, tot_pc = 0, tot_visit = 0;
     int g_first, g_cnt;
@@ -858,7 +860,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         int q = 0, k = 0;
         int2 cur = make_int2(0, 0);
         unsigned near = 0;
-        if (nlq > 0) cur = sm.lq[0][lane];
+        if (nlq > 0) cur = lq[0];
         while (q < nlq) {
             const int j = cur.x + k;
             const double4 pj = ldg4(&posm[j]);
@@ -879,18 +881,18 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             }
             if (++k == cur.y) {
                 n_pp += k;
-                sm.near[q][lane] = near;
+                nearq[q * 32] = near;
                 near = 0;
                 k = 0;
                 ++q;
-                if (q < nlq) cur = sm.lq[q][lane];
+                if (q < nlq) cur = lq[q * 32];
             }
         }
         q = 0;
         near = 0;
         int first = 0;
         for (;;) {
-            while (near == 0 && q < nlq) { near = sm.near[q][lane]; first = sm.lq[q][lane].x; ++q; }
+            while (near == 0 && q < nlq) { near = nearq[q * 32]; first = lq[q * 32].x; ++q; }
             if (near == 0) break;
             const int j = first + __ffs(near) - 1;
             near &= near - 1;
@@ -917,7 +919,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     auto queue_leaf = [&](bool me, int first, int count) {
         const int last = first + count;
         for (int base = first; base < last; base += 32) {
-            if (me) { sm.lq[nlq][lane] = make_int2(base, min(32, last - base)); ++nlq; }
+            if (me) { lq[nlq * 32] = make_int2(base, min(32, last - base)); ++nlq; }
             if (__any_sync(SPHB_FULL_MASK, nlq == GRAV_LQ)) flush_pp();
         }
     };

@@ -311,7 +311,7 @@ __global__ void k_tree_scatter(TreeBuild t, TreeDev o, int n_nodes, const double
 // groups are cut at the boundaries of "group cells": the tree nodes with <= GROUP_CELL_MAX particles
 // whose parent has more (and leaves above that size at the maximum level).  A group cell is chopped
 // into slices of 32; every group therefore lies inside one cube holding <= GROUP_CELL_MAX particles.
-constexpr int GROUP_CELL_MAX = 128;
+constexpr int GROUP_CELL_MAX = 512;
 
 __global__ void k_group_flags(TreeBuild t, int n_nodes, unsigned char * __restrict__ flags, int slice_len, int n)
 {
