@@ -78,11 +78,12 @@ template <int DIM> __device__ __forceinline__ void vec_from4(const double4 & q, 
 // =================================================================================================
 template <int DIM, int KT>
 struct InitSmoothV {
-    const DevParams & P;
+    const DevParams & P; const double4 * posm;
     double ri[DIM], h, h2, dens;
     KernelCoef<DIM, KT> kc;
-    __device__ __forceinline__ void hit(int, const double4 & pj, double)
+    __device__ __forceinline__ void hit(int j)
     {
+        const double4 pj = ldg4(&posm[j]);
         double d[DIM];
         rij_from4<DIM>(P, ri, pj, d);
         const double r2 = abs2_exact<DIM>(d);
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, Recs rc, Tree
     while (next_group(gt, lane, g_first, g_cnt)) {
     const int i = g_first + lane;
     const bool valid = lane < g_cnt;
-    InitSmoothV<DIM, KT> v{P};
+    InitSmoothV<DIM, KT> v{P, rc.posm};
     v.dens = 0.0;
     v.h = 1.0;
     if (valid) {
@@ -124,25 +125,14 @@ __global__ void __launch_bounds__(128) k_initial_smoothing(PSoA p, Recs rc, Tree
 // =================================================================================================
 // candidate set {j : r2 < h_search^2} (src/bhtree.cpp:251-261) -> per-lane columns r, j (and m) in
 // the warp's scratch slot (column layout [k][lane]: every later pass reads them coalesced)
-template <int DIM, bool NEED_M>
-struct CollectV {
-    const DevParams & P;
-    double ri[DIM], hs2;
-    double * lr; double * lm; int * lj;
+// per-lane index column in the warp's scratch slot (layout [k][lane]: later passes read it coalesced)
+struct IndexListV {
+    int * lj;
     int cap, cnt, lane;
-    __device__ __forceinline__ void hit(int j, const double4 & pj, double)
+    __device__ __forceinline__ void hit(int j)
     {
-        double d[DIM];
-        rij_from4<DIM>(P, ri, pj, d);
-        const double r2 = abs2_exact<DIM>(d);
-        if (r2 < hs2) {
-            if (cnt < cap) {
-                lr[cnt * 32 + lane] = sqrt(r2);
-                lj[cnt * 32 + lane] = j;
-                if (NEED_M) lm[cnt * 32 + lane] = pj.w;
-            }
-            ++cnt;
-        }
+        if (cnt < cap) lj[cnt * 32 + lane] = j;
+        ++cnt;
     }
 };
 
@@ -264,19 +254,37 @@ k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
         const double hs2 = __dmul_rn(hs, hs);
         double h = hs;
 
-        // ---- candidates (src/pre_interaction.cpp:66-71)
-        int ncand;
+        // ---- candidates (src/pre_interaction.cpp:66-71): conservative hits of the group search ...
+        int nraw;
         {
-            CollectV<DIM, NEED_M> cv{P};
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) cv.ri[d] = ri[d];
-            cv.hs2 = hs2; cv.lr = lr; cv.lm = lm; cv.lj = lj; cv.cap = P.list_cap; cv.cnt = 0; cv.lane = lane;
+            IndexListV cv{lj, P.list_cap, 0, lane};
             group_stream<DIM, false>(t, P, rc.posm, nullptr, 0, sm, lane, ri, hs, valid, cv, d_err);
-            ncand = cv.cnt;
+            nraw = valid ? cv.cnt : 0;
         }
-        if (ncand > P.list_cap) { ++c_over; ncand = P.list_cap; }
-        c_cand += valid ? ncand : 0;
+        if (nraw > P.list_cap) { ++c_over; nraw = P.list_cap; }
         __syncwarp();
+        // ... reduced to the candidate set {j : r2 < h_search^2} (src/bhtree.cpp:251-261) by the exact test,
+        // all lanes together; columns r, j (and m) are compacted in place
+        int ncand = 0;
+        {
+            const int nraw_max = __reduce_max_sync(SPHB_FULL_MASK, nraw);
+            for (int k = 0; k < nraw_max; ++k) {
+                if (k < nraw) {
+                    const int j = lj[k * 32 + lane];
+                    const double4 pj = ldg4(&rc.posm[j]);
+                    double d[DIM];
+                    rij_from4<DIM>(P, ri, pj, d);
+                    const double r2 = abs2_exact<DIM>(d);
+                    if (r2 < hs2) {
+                        lr[ncand * 32 + lane] = sqrt(r2);
+                        lj[ncand * 32 + lane] = j;
+                        if (NEED_M) lm[ncand * 32 + lane] = pj.w;
+                        ++ncand;
+                    }
+                }
+            }
+        }
+        c_cand += ncand;
         const int ncand_max = __reduce_max_sync(SPHB_FULL_MASK, ncand);
 
         if (P.iterative) {
@@ -498,24 +506,8 @@ __device__ __forceinline__ void hll(const double (&left)[4], const double (&righ
 }
 
 // pair set of lane i: {j : 0 < r < max(h_i, h_j)} (src/fluid_force.cpp:62; the reference's candidate
-// test r2 < max(h_i, kernel_size(leaf))^2, src/bhtree.cpp:255-256, is implied by it) -> j column
-template <int DIM>
-struct PairCollectV {
-    const DevParams & P;
-    double ri[DIM], h_i;
-    int * lj;
-    int cap, cnt, lane;
-    __device__ __forceinline__ void hit(int j, const double4 & pj, double h_j)
-    {
-        double d[DIM];
-        rij_from4<DIM>(P, ri, pj, d);
-        const double r = sqrt(abs2_exact<DIM>(d));
-        if (r >= fmax(h_i, h_j) || r == 0.0) return;
-        if (cnt < cap) lj[cnt * 32 + lane] = j;
-        ++cnt;
-    }
-};
-
+// test r2 < max(h_i, kernel_size(leaf))^2, src/bhtree.cpp:255-256, is implied by it).  The group search
+// records the conservative hits (IndexListV); ForceAcc::pair applies this exact filter first.
 template <int DIM, int KT, int SPH>
 struct ForceAcc {
     const DevParams & P; const PSoA & p; const Recs & rc;
@@ -528,16 +520,19 @@ struct ForceAcc {
     double m_u_inv;         // DISPH: 1/(m_i u_i)
     KernelCoef<DIM, KT> ki;
     double acc[DIM], dene;
+    unsigned int pairs;
 
     __device__ __forceinline__ void pair(int j)
     {
         const double4 pj = ldg4(&rc.posm[j]);
-        const double4 vc = ldg4(&rc.velc[j]);
         const double4 th = ldg4(&rc.thermo[j]);          // {u, h, dens, pres}
         double d[DIM];
         rij_from4<DIM>(P, ri, pj, d);
         const double r = sqrt(abs2_exact<DIM>(d));
         const double h_j = th.y;
+        if (r >= fmax(h_i, h_j) || r == 0.0) return;     // src/fluid_force.cpp:62
+        ++pairs;
+        const double4 vc = ldg4(&rc.velc[j]);
         KernelCoef<DIM, KT> kj;
         kj.init(h_j);
         const double cwi = ki.dwc(r), cwj = kj.dwc(r);
@@ -664,6 +659,7 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
         v.i = i;
         v.dt = dt;
         v.dene = 0.0;
+        v.pairs = 0;
 #pragma unroll
         for (int a = 0; a < DIM; ++a) { v.acc[a] = 0.0; v.ri[a] = 0.0; v.vi[a] = 0.0; }
         v.h_i = 1.0; v.m_i = 1.0; v.dens_i = 1.0; v.pres_i = 1.0; v.gradh_i = 0.0; v.alpha_i = 0.0; v.bal_i = 0.0; v.c_i = 0.0; v.u_i = 1.0;
@@ -696,16 +692,12 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
         // ---- symmetric pair search
         int npair;
         {
-            PairCollectV<DIM> cv{P};
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) cv.ri[a] = v.ri[a];
-            cv.h_i = v.h_i; cv.lj = lj; cv.cap = P.list_cap; cv.cnt = 0; cv.lane = lane;
+            IndexListV cv{lj, P.list_cap, 0, lane};
             group_stream<DIM, true>(t, P, rc.posm, reinterpret_cast<const double *>(rc.thermo) + 1, 4, sm, lane, v.ri, v.h_i, valid, cv, d_err);
             npair = cv.cnt;
         }
         if (npair > P.list_cap) { ++c_over; npair = P.list_cap; }
         if (!valid) npair = 0;
-        c_pairs += npair;
         __syncwarp();
         const int npair_max = __reduce_max_sync(SPHB_FULL_MASK, npair);
         // ---- pair bodies, all lanes together
@@ -716,6 +708,7 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 #pragma unroll
             for (int a = 0; a < DIM; ++a) p.acc[a][i] = v.acc[a];
             p.dene[i] = v.dene;
+            c_pairs += v.pairs;
         }
         __syncwarp();
     }
@@ -1289,13 +1282,15 @@ struct ListV {
     int cnt;
     int * out;           // fill: write p.orig[j] at out[cnt]
     long long cap_left;
-    __device__ __forceinline__ void hit(int j, const double4 & pj, double hj)
+    const double4 * posm;
+    __device__ __forceinline__ void hit(int j)
     {
+        const double4 pj = ldg4(&posm[j]);
         double d[DIM];
         rij_from4<DIM>(P, ri, pj, d);
         const double r2 = abs2_exact<DIM>(d);
         double k2 = h_i2;
-        if (symmetric) k2 = fmax(h_i2, __dmul_rn(hj, hj));     // exhaustive_search.cpp:28
+        if (symmetric) { const double hj = p.sml[j]; k2 = fmax(h_i2, __dmul_rn(hj, hj)); }     // exhaustive_search.cpp:28
         if (r2 < k2) {
             if (fill && cnt < cap_left) out[cnt] = p.orig[j];
             ++cnt;
@@ -1316,6 +1311,7 @@ k_neighbor_lists(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt, const d
     const int i = g_first + lane;
     const bool valid = lane < g_cnt;
     ListV<DIM> v{P, p};
+    v.posm = rc.posm;
     v.symmetric = symmetric != 0; v.fill = fill != 0; v.cnt = 0; v.out = nullptr; v.cap_left = 0;
     double h_i = 1.0;
 #pragma unroll

@@ -8,13 +8,13 @@
 //      max(radius, BHNode::kernel_size of the node), src/bhtree.cpp:237).  Children of hit nodes are
 //      pushed, hit leaves are streamed.  No per-particle pointer chasing, 32 node loads in flight.
 //   2. Candidate streaming: the particles of the hit leaves are staged 32 at a time into a
-//      shared-memory tile ({x,y,z,m} FP64 + a group-relative FP32 copy); every lane runs the SAME
-//      loop over the tile (convergent, broadcast reads) with a conservative FP32 distance test that
-//      only produces a hit mask; the FP32 pipe is otherwise idle in this code and runs at twice the
-//      FP64 rate.
-//   3. Each lane passes its (few) hits to the visitor, which applies the reference's exact FP64
-//      predicate (r2 < h2 with the reference's operation order) — so the neighbour SET is exactly
-//      the reference's; the tree and the FP32 test only ever discard pairs that cannot pass.
+//      shared-memory tile (group-relative FP32 coordinates); every lane runs the SAME loop over the
+//      tile (convergent, broadcast reads) with a conservative FP32 distance test that only produces
+//      a hit mask; the FP32 pipe is otherwise idle in this code and runs at twice the FP64 rate.
+//   3. Each lane hands the indices of its (few) hits to the visitor; the caller then applies the
+//      reference's exact FP64 predicate (r2 < h2 with the reference's operation order) in a
+//      convergent pass over the recorded indices — so the neighbour SET is exactly the
+//      reference's; the tree and the FP32 test only ever discard pairs that cannot pass.
 // The cull is conservative by construction (margins below), hence the set equals the
 // EXHAUSTIVE_SEARCH set, which the reference's tree search reproduces as well.
 #pragma once
@@ -27,10 +27,8 @@ constexpr int NW_STACK = 512;      // node stack entries per warp
 struct NWalkSmem {
     int     stack[NW_STACK];       // child0 | (nchild - 1) << 29: all children of a hit node
     int     expand[32];            // nodes of the batch being fetched
-    double4 tile64[32];            // {x, y, z, m} of the staged candidates
-    float4  tile32[32];            // {x - ref, y - ref, z - ref, symmetric threshold} in FP32
-    double  tileh[32];             // h_j (symmetric search only)
-    int     tilej[32];             // particle index
+    float4  tile32[32];            // staged candidates: {x - ref, y - ref, z - ref, symmetric threshold} in FP32
+    int     tilej[32];             //   particle index
 };
 
 // error bits reported through d_err[2]
@@ -59,7 +57,7 @@ template <int DIM> struct Filter32 {
     double delta;         // absolute per-axis error bound of the FP32 coordinates inside rlim
 };
 
-// V:  void hit(int j, const double4 & pj, double hj)   — lane's conservative hit; exact test inside.
+// V:  void hit(int j)   — particle j passed lane's conservative test; the exact test is the caller's.
 // reach = search radius of the group (max over lanes), h_i = lane's own radius (gather: h_search,
 // symmetric: sml_i).  hj_src / hj_stride: where h_j lives for the symmetric search.
 template <int DIM, bool SYM, class V>
@@ -129,49 +127,51 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
         while (hits) {
             const int kb = __ffs(hits) - 1;
             hits &= hits - 1;
-            v.hit(sm.tilej[kb], sm.tile64[kb], SYM ? sm.tileh[kb] : 0.0);
+            v.hit(sm.tilej[kb]);
         }
     };
 
-    // stage particles [first, first + count) of a hit leaf, processing tiles as they fill up
+    // FP32 image of the m candidates whose indices sit in sm.tilej
+    auto stage = [&](int m) {
+        __syncwarp();
+        if (lane < m) {
+            const int j = sm.tilej[lane];
+            const double4 pj = ldg4(&posm[j]);
+            double dj[DIM];
+            dj[0] = pj.x - F.ref[0];
+            if (DIM >= 2) dj[DIM >= 2 ? 1 : 0] = pj.y - F.ref[DIM >= 2 ? 1 : 0];
+            if (DIM >= 3) dj[DIM >= 3 ? 2 : 0] = pj.z - F.ref[DIM >= 3 ? 2 : 0];
+            double amax = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                if (P.periodic) dj[d] = min_image(dj[d], P.range[d]);
+                amax = fmax(amax, fabs(dj[d]));
+            }
+            float4 f = make_float4((float)dj[0], DIM >= 2 ? (float)dj[DIM >= 2 ? 1 : 0] : 0.f,
+                                   DIM >= 3 ? (float)dj[DIM >= 3 ? 2 : 0] : 0.f, -1.0f);
+            if (SYM) {
+                const double hj = __ldg(hj_src + (size_t)j * hj_stride);
+                const double dl = 1.1920929e-7 * (fmax(amax, F.rlim) + lmax);
+                const double hh = hj + 4.0 * (dl + F.delta);
+                f.w = (float)(hh * hh * (1.0 + 4e-6));
+            } else if (amax > F.rlim) {
+                f.x = 3e18f;                         // cannot be within h_search of any lane
+            }
+            sm.tile32[lane] = f;
+        }
+        __syncwarp();
+    };
+    // queue the particles [first, first + count) of a hit leaf; full tiles are staged and tested
     auto feed = [&](int first, int count) {
         int off = 0;
         while (off < count) {
             const int take = min(count - off, 32 - fill);
-            if (lane >= fill && lane < fill + take) {
-                const int j = first + off + (lane - fill);
-                const double4 pj = ldg4(&posm[j]);
-                double dj[DIM];
-                dj[0] = pj.x - F.ref[0];
-                if (DIM >= 2) dj[DIM >= 2 ? 1 : 0] = pj.y - F.ref[DIM >= 2 ? 1 : 0];
-                if (DIM >= 3) dj[DIM >= 3 ? 2 : 0] = pj.z - F.ref[DIM >= 3 ? 2 : 0];
-                double amax = 0.0;
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) {
-                    if (P.periodic) dj[d] = min_image(dj[d], P.range[d]);
-                    amax = fmax(amax, fabs(dj[d]));
-                }
-                float4 f = make_float4((float)dj[0], DIM >= 2 ? (float)dj[DIM >= 2 ? 1 : 0] : 0.f,
-                                       DIM >= 3 ? (float)dj[DIM >= 3 ? 2 : 0] : 0.f, -1.0f);
-                if (SYM) {
-                    const double hj = __ldg(hj_src + (size_t)j * hj_stride);
-                    const double dl = 1.1920929e-7 * (fmax(amax, F.rlim) + lmax);
-                    const double hh = hj + 4.0 * (dl + F.delta);
-                    f.w = (float)(hh * hh * (1.0 + 4e-6));
-                    sm.tileh[lane] = hj;
-                } else if (amax > F.rlim) {
-                    f.x = 3e18f;                         // cannot be within h_search of any lane
-                }
-                sm.tile64[lane] = pj;
-                sm.tile32[lane] = f;
-                sm.tilej[lane] = j;
-            }
+            if (lane < take) sm.tilej[fill + lane] = first + off + lane;
             fill += take;
             off += take;
             if (fill == 32) {
-                __syncwarp();
+                stage(32);
                 process(32);
-                __syncwarp();
                 fill = 0;
             }
         }
@@ -254,7 +254,7 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
         }
     }
     if (fill > 0) {
-        __syncwarp();
+        stage(fill);
         process(fill);
     }
     __syncwarp();
