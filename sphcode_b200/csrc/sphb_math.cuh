@@ -231,6 +231,18 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SPHB_FULL_MASK, v, o);
     return v;
 }
+// 32 x 32 bit-matrix transpose across a warp: lane k passes row k, lane j receives column j
+// (bit k of the result = bit j of lane k's input).  Five butterfly steps.
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane)
+{
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const unsigned m = s == 16 ? 0x0000ffffu : s == 8 ? 0x00ff00ffu : s == 4 ? 0x0f0f0f0fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(SPHB_FULL_MASK, x, s);
+        x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y & m) << s));
+    }
+    return x;
+}
 // Non-negative doubles order like their bit patterns: min / max through 64-bit integer atomics.
 __device__ __forceinline__ void atomic_min_pos(double * addr, double v)
 {

@@ -741,7 +741,8 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 //     read through L1; lanes of a warp are Morton neighbours and share these lines).
 constexpr int GRAV_LQ = 64;       // leaf queue depth per lane (global scratch, [entry][lane])
 constexpr int GV_STACK = 704;     // node stack entries per warp (<= 28 stay behind per tree level, see pop_load)
-constexpr int GV_PC = 64;         // accepted cells per chunk
+constexpr int GV_NB = 4;          // batches of accepted cells per chunk
+constexpr int GV_PC = 32 * GV_NB; // chunk slots: slot = 32 * block + lane of the node in its batch
 
 struct GravSmem {
     int2     stack[GV_STACK];           // {child0 | (nchild - 1) << 29, lane mask}: the children of an opened node
@@ -802,8 +803,8 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     const double einv_i = 2.0 / h_i;
     const double h_i2 = h_i * h_i * (1.0 + 1e-12);   // near test: r2 < max(h_i, h_j)^2 with a margin
     unsigned int n_pp = 0, n_pc = 0, n_visit = 0;             // per lane: fit 32 bits
-    unsigned pc_lo = 0, pc_hi = 0;                           // lane's accept bits over the chunk (entries 0-31, 32-63)
-    int npc = 0, nlq = 0;
+    unsigned pcw0 = 0, pcw1 = 0, pcw2 = 0, pcw3 = 0;         // lane's accept bits over the 4 blocks of the chunk
+    int npb = 0, nlq = 0;                                    // blocks in use
 
     double bc[DIM], bh[DIM];
     group_box<DIM>(ri, valid, bc, bh);
@@ -812,11 +813,11 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     // accepted cells of the current chunk: monopole, src/bhtree.cpp:326-330; two cells in flight
     auto flush_pc = [&]() {
         __syncwarp();
-        n_pc += __popc(pc_lo) + __popc(pc_hi);
+        n_pc += __popc(pcw0) + __popc(pcw1) + __popc(pcw2) + __popc(pcw3);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            unsigned mm = half ? pc_hi : pc_lo;
-            const double * px = sm.pcx + half * 32, * py = sm.pcy + half * 32, * pz = sm.pcz + half * 32, * pm = sm.pcm + half * 32;
+        for (int blk = 0; blk < GV_NB; ++blk) {
+            unsigned mm = blk == 0 ? pcw0 : blk == 1 ? pcw1 : blk == 2 ? pcw2 : pcw3;
+            const double * px = sm.pcx + blk * 32, * py = sm.pcy + blk * 32, * pz = sm.pcz + blk * 32, * pm = sm.pcm + blk * 32;
             while (mm) {
                 const int e0 = __ffs(mm) - 1;
                 mm &= mm - 1;
@@ -838,12 +839,9 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
             }
         }
-        pc_lo = pc_hi = 0;
-        npc = 0;
+        pcw0 = pcw1 = pcw2 = pcw3 = 0;
+        npb = 0;
         __syncwarp();
-    };
-    auto pc_set = [&](unsigned bit, int e) {                 // bit (0/1) of this lane for chunk entry e
-        if (e < 32) pc_lo |= bit << e; else pc_hi |= bit << (e - 32);
     };
     // queued leaves: particle-particle sums of src/bhtree.cpp:309-317.  Pass 1 runs one flattened
     // loop over all particles of the lane's queued leaves with the unsoftened form (u >= 2 for both
@@ -1025,28 +1023,16 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             sm.minfo[slot] = make_int4(child0, nchild, first, count);
             sm.mmask[slot] = mask;
         }
-        // (c) accepted by every lane of the mask -> chunk
-        {
-            unsigned ba = b_acc;
-            while (ba) {
-                const int take = min(GV_PC - npc, __popc(ba));
-                const int rank = __popc(ba & lt_mask);
-                if (((ba >> lane) & 1u) && rank < take) {
-                    const int e = npc + rank;
-                    sm.pcx[e] = c[0];
-                    if (DIM >= 2) sm.pcy[e] = c[DIM >= 2 ? 1 : 0];
-                    if (DIM >= 3) sm.pcz[e] = c[DIM >= 3 ? 2 : 0];
-                    sm.pcm[e] = P.G * mass;
-                }
-                for (int r = 0; r < take; ++r) {
-                    const int src = __ffs(ba) - 1;
-                    ba &= ba - 1;
-                    const unsigned m = __shfl_sync(SPHB_FULL_MASK, mask, src);
-                    pc_set((m >> lane) & 1u, npc + r);
-                }
-                npc += take;
-                if (npc == GV_PC) flush_pc();
-            }
+        // (c) cells somebody accepts (class 1: every lane of the mask; class 3: decided below) get the
+        // chunk slot {block npb, this lane}; racc = lanes that accept this lane's node
+        unsigned racc = cls == 1 ? mask : 0u;
+        const int mslot = __popc(b_mix & lt_mask);         // class 3: position in the mixed list
+        if (cls == 1 || cls == 3) {
+            const int e = npb * 32 + lane;
+            sm.pcx[e] = c[0];
+            if (DIM >= 2) sm.pcy[e] = c[DIM >= 2 ? 1 : 0];
+            if (DIM >= 3) sm.pcz[e] = c[DIM >= 3 ? 2 : 0];
+            sm.pcm[e] = P.G * mass;
         }
         // (b) opened by every lane of the mask, leaf -> per-lane queues
         {
@@ -1080,16 +1066,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             }
             const unsigned a_b = __ballot_sync(SPHB_FULL_MASK, accept);
             const unsigned o_b = __ballot_sync(SPHB_FULL_MASK, open);
-            if (a_b) {
-                pc_set(accept ? 1u : 0u, npc);
-                if (lane == 0) {
-                    sm.pcx[npc] = c4.x;
-                    if (DIM >= 2) sm.pcy[npc] = c4.y;
-                    if (DIM >= 3) sm.pcz[npc] = c4.z;
-                    sm.pcm[npc] = P.G * c4.w;
-                }
-                if (++npc == GV_PC) flush_pc();
-            }
+            if (cls == 3 && mslot == q) racc = a_b;        // the node's own lane keeps its accept mask
             if (o_b) {
                 if (info.y == 0) {
                     queue_leaf(open, info.z, info.w);
@@ -1100,6 +1077,12 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                     top += 1;
                 }
             }
+        }
+        // accept masks of the batch, node-major -> particle-major: one word per lane for block npb
+        if (b_acc | b_mix) {
+            const unsigned tw = warp_transpose32(racc, lane);
+            if (npb == 0) pcw0 = tw; else if (npb == 1) pcw1 = tw; else if (npb == 2) pcw2 = tw; else pcw3 = tw;
+            if (++npb == GV_NB) flush_pc();
         }
         __syncwarp();
     }
