@@ -92,7 +92,7 @@ struct sphb_ctx {
     bool first_pre = true;
     unsigned long long nonconverged_total = 0;
 
-    double * scratch_r = nullptr, * scratch_m = nullptr; int * scratch_j = nullptr; int pre_grid = 0;
+    double * scratch_r = nullptr, * scratch_m = nullptr; int * scratch_j = nullptr; int pre_grid = 0, grav_grid = 0;
     unsigned char * grp_flags = nullptr;   // 1 where a group starts (tree order)
     int * grp_start = nullptr;             // first particle of every group, ascending
     int * d_ngroups = nullptr;             // number of groups (device)
@@ -212,7 +212,8 @@ int alloc_particles(sphb_ctx * c, int n)
     if (dev_alloc(c, &c->d_bbox_part, (size_t)c->bbox_blocks * 6, c->allocs)) return 1;
 
     // list scratch: one r, j (and m) column set per resident warp of the persistent pre / force kernels
-    c->pre_grid = std::min(cdiv(groups, 4), c->sm_count * 4);
+    c->pre_grid = std::min(cdiv(groups, 4), c->sm_count * 5);       // pre / force: 5 resident blocks per SM
+    c->grav_grid = std::min(cdiv(groups, 4), c->sm_count * 4);      // gravity: 4
     const size_t slots = (size_t)c->pre_grid * 4;
     if (dev_alloc(c, &c->scratch_r, slots * c->P.list_cap * 32, c->allocs)) return 1;
     if (dev_alloc(c, &c->scratch_j, slots * c->P.list_cap * 32, c->allocs)) return 1;
@@ -566,7 +567,7 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
         if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
         static bool attr_set = false;
         if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(GravSmem)))); attr_set = true; }
-        k_gravity<DIM><<<c->pre_grid, 128, 4 * sizeof(GravSmem), c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, c->grav_lq, c->grav_near, c->counters_on ? c->d_cnt : nullptr, c->d_err);
+        k_gravity<DIM><<<c->grav_grid, 128, 4 * sizeof(GravSmem), c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, c->grav_lq, c->grav_near, c->counters_on ? c->d_cnt : nullptr, c->d_err);
         LAUNCH_CHECK();
     }
     return 0;

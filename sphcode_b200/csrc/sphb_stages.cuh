@@ -217,7 +217,7 @@ struct DensityAcc {
 };
 
 template <int DIM, int KT, int SPH>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
                   double * __restrict__ scratch_r, double * __restrict__ scratch_m, int * __restrict__ scratch_j,
                   const double * __restrict__ d_dt, double * __restrict__ d_hpvs,
@@ -637,7 +637,7 @@ struct ForceAcc {
 };
 
 template <int DIM, int KT, int SPH>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
               int * __restrict__ scratch_j, const double * __restrict__ d_dt,
               unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt)
@@ -741,7 +741,7 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 //     read through L1; lanes of a warp are Morton neighbours and share these lines).
 constexpr int GRAV_LQ = 64;       // leaf queue depth per lane (global scratch, [entry][lane])
 constexpr int GV_STACK = 704;     // node stack entries per warp (<= 28 stay behind per tree level, see pop_load)
-constexpr int GV_NB = 4;          // batches of accepted cells per chunk
+constexpr int GV_NB = 2;          // batches of accepted cells per chunk
 constexpr int GV_PC = 32 * GV_NB; // chunk slots: slot = 32 * block + lane of the node in its batch
 
 struct GravSmem {
@@ -803,7 +803,9 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     const double einv_i = 2.0 / h_i;
     const double h_i2 = h_i * h_i * (1.0 + 1e-12);   // near test: r2 < max(h_i, h_j)^2 with a margin
     unsigned int n_pp = 0, n_pc = 0, n_visit = 0;             // per lane: fit 32 bits
-    unsigned pcw0 = 0, pcw1 = 0, pcw2 = 0, pcw3 = 0;         // lane's accept bits over the 4 blocks of the chunk
+    unsigned pcw[GV_NB];                                     // lane's accept bits over the blocks of the chunk
+#pragma unroll
+    for (int b = 0; b < GV_NB; ++b) pcw[b] = 0;
     int npb = 0, nlq = 0;                                    // blocks in use
 
     double bc[DIM], bh[DIM];
@@ -813,10 +815,10 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     // accepted cells of the current chunk: monopole, src/bhtree.cpp:326-330; two cells in flight
     auto flush_pc = [&]() {
         __syncwarp();
-        n_pc += __popc(pcw0) + __popc(pcw1) + __popc(pcw2) + __popc(pcw3);
 #pragma unroll
         for (int blk = 0; blk < GV_NB; ++blk) {
-            unsigned mm = blk == 0 ? pcw0 : blk == 1 ? pcw1 : blk == 2 ? pcw2 : pcw3;
+            unsigned mm = pcw[blk];
+            n_pc += __popc(mm);
             const double * px = sm.pcx + blk * 32, * py = sm.pcy + blk * 32, * pz = sm.pcz + blk * 32, * pm = sm.pcm + blk * 32;
             while (mm) {
                 const int e0 = __ffs(mm) - 1;
@@ -839,7 +841,8 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
             }
         }
-        pcw0 = pcw1 = pcw2 = pcw3 = 0;
+#pragma unroll
+        for (int b = 0; b < GV_NB; ++b) pcw[b] = 0;
         npb = 0;
         __syncwarp();
     };
@@ -1081,7 +1084,8 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         // accept masks of the batch, node-major -> particle-major: one word per lane for block npb
         if (b_acc | b_mix) {
             const unsigned tw = warp_transpose32(racc, lane);
-            if (npb == 0) pcw0 = tw; else if (npb == 1) pcw1 = tw; else if (npb == 2) pcw2 = tw; else pcw3 = tw;
+#pragma unroll
+            for (int b = 0; b < GV_NB; ++b) if (npb == b) pcw[b] = tw;
             if (++npb == GV_NB) flush_pc();
         }
         __syncwarp();
