@@ -208,6 +208,9 @@ typedef struct sphb_counters {
     uint64_t grav_node_visits;  /* node opening tests, reference semantics per particle */
     uint64_t tree_nodes;
     uint64_t tree_leaves;
+    uint64_t grav_pc_group;     /* of grav_pc: cells accepted by every particle of the walking group */
+    uint64_t grav_pp_group;     /* of grav_pp: leaves opened by every particle of the walking group  */
+    uint64_t n_groups;          /* particle groups (walk work units) of the current tree             */
 } sphb_counters;
 /* enable != 0 makes the stage kernels count (slower); read with sphb_get_counters. */
 int sphb_enable_counters(sphb_ctx *ctx, int enable);

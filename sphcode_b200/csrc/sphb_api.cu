@@ -97,7 +97,7 @@ struct sphb_ctx {
     int * grp_start = nullptr;             // first particle of every group, ascending
     int * d_ngroups = nullptr;             // number of groups (device)
     int * d_grp_ctl = nullptr;             // [0] work counter, [1] end group of the current kernel
-    int2 * grav_lq = nullptr; unsigned * grav_near = nullptr;   // per-warp leaf queues of the gravity walk
+    double2 * grav_lq = nullptr; int * grav_near = nullptr;   // per-warp leaf queues of the gravity walk
     Recs rc{};                             // packed gather records (tree order)
     bool recs_dirty = true;                // SoA fields changed since the records were packed
 
@@ -106,6 +106,7 @@ struct sphb_ctx {
 
     bool counters_on = false, timers_on = false;
     sphb_counters last_counters{};
+    int last_ngroups = 0;
     cudaEvent_t ev[2 * SPHB_T_COUNT] = {};
     float ms[SPHB_T_COUNT] = {};
     bool ev_used[SPHB_T_COUNT] = {};
@@ -221,7 +222,7 @@ int alloc_particles(sphb_ctx * c, int n)
     else c->scratch_m = nullptr;
     if (dev_alloc(c, &c->grp_flags, np + 32, c->allocs) || dev_alloc(c, &c->grp_start, np + 32, c->allocs)) return 1;
     if (c->P.use_gravity) {
-        if (dev_alloc(c, &c->grav_lq, slots * GRAV_LQ * 32, c->allocs) || dev_alloc(c, &c->grav_near, slots * GRAV_LQ * 32, c->allocs)) return 1;
+        if (dev_alloc(c, &c->grav_lq, slots * GRAV_LQ * 32, c->allocs) || dev_alloc(c, &c->grav_near, slots * GRAV_NEAR * 32, c->allocs)) return 1;
     }
     // packed gather records
     if (dev_alloc(c, &c->rc.posm, np, c->allocs) || dev_alloc(c, &c->rc.velc, np, c->allocs) ||
@@ -563,6 +564,7 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
     if (s.n_local > 0) {
         if (ensure_recs(c)) return 1;
         k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, c->rc.hsoft, c->n); LAUNCH_CHECK();
+        k_grav_leaf_h<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td, c->cur.sml); LAUNCH_CHECK();
         GroupTable gt;
         if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
         static bool attr_set = false;
@@ -1094,6 +1096,9 @@ int sphb_get_counters(sphb_ctx * c, sphb_counters * out)
     o.newton_evals = h.newton_evals; o.newton_iters = h.newton_iters;
     o.pre_candidates = h.pre_candidates; o.pre_neighbors = h.pre_neighbors;
     o.force_pairs = h.force_pairs; o.grav_pp = h.grav_pp; o.grav_pc = h.grav_pc; o.grav_node_visits = h.grav_node_visits;
+    o.grav_pc_group = h.grav_pc_group; o.grav_pp_group = h.grav_pp_group;
+    CK(cudaMemcpy(&c->last_ngroups, c->d_ngroups, sizeof(int), cudaMemcpyDeviceToHost));
+    o.n_groups = (uint64_t)c->last_ngroups;
     if (c->tree_valid) {
         std::vector<double2> nn((size_t)c->td.n_nodes * 4);
         CK(cudaMemcpy(nn.data(), c->td.nn, nn.size() * sizeof(double2), cudaMemcpyDeviceToHost));

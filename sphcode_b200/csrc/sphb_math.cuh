@@ -198,12 +198,14 @@ __device__ __forceinline__ double fast_rsqrt(double x)
     return fma(y, e * p, y);
 }
 
-// read-only 32-byte load (no double4 overload of __ldg): two 16-byte non-coherent loads
+// read-only 32-byte load: ONE 256-bit non-coherent load (sm_100a: LDG.E.ENL2.256.CONSTANT), i.e. one
+// L1 wavefront per distinct record instead of the two of a pair of 16-byte loads.  p must be 32-byte
+// aligned (the packed record arrays are).
 __device__ __forceinline__ double4 ldg4(const double4 * p)
 {
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    return make_double4(a.x, a.y, b.x, b.y);
+    double4 v;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
 }
 
 // ---- warp / atomic helpers -------------------------------------------------------------------

@@ -18,7 +18,8 @@ namespace sphb {
 
 struct Counters {   // device mirror of sphb_counters (include/sphb.h), all summed over particles
     unsigned long long newton_evals, newton_iters, pre_candidates, pre_neighbors, force_pairs,
-                       grav_pp, grav_pc, grav_node_visits, nonconverged, list_overflow;
+                       grav_pp, grav_pc, grav_node_visits, nonconverged, list_overflow,
+                       grav_pc_group, grav_pp_group;
 };
 
 template <int DIM> __device__ __forceinline__ void load_vec(double * const (&a)[3], int i, double (&o)[DIM])
@@ -740,6 +741,7 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 //     lane runs one flattened loop over all particles of its queued leaves (packed x,y,z,m + 2/h
 //     read through L1; lanes of a warp are Morton neighbours and share these lines).
 constexpr int GRAV_LQ = 64;       // leaf queue depth per lane (global scratch, [entry][lane])
+constexpr int GRAV_NEAR = 128;    // softened-pair list depth per lane (global scratch, [entry][lane])
 constexpr int GV_STACK = 704;     // node stack entries per warp (<= 28 stay behind per tree level, see pop_load)
 constexpr int GV_NB = 2;          // batches of accepted cells per chunk
 constexpr int GV_PC = 32 * GV_NB; // chunk slots: slot = 32 * block + lane of the node in its batch
@@ -751,6 +753,7 @@ struct GravSmem {
     double4  mx[32];                    // mixed nodes of the current batch: mass centre + mass
     double   me2[32];                   //   edge^2
     int4     minfo[32];                 //   {child0, nchild, first, count}
+    double   mh2[32];                   //   leaves: largest h^2 among the leaf's particles (k_grav_leaf_h)
     unsigned mmask[32];                 //   lane mask
 };
 
@@ -776,18 +779,19 @@ __device__ __forceinline__ void soft_fg_fast(double r, double rinv, double einv,
 template <int DIM>
 __global__ void __launch_bounds__(128, 4)
 k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restrict__ posm,
-          const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, int2 * __restrict__ scratch_lq,
-          unsigned * __restrict__ scratch_near, Counters * __restrict__ cnt, unsigned long long * __restrict__ d_err)
+          const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, double2 * __restrict__ scratch_lq,
+          int * __restrict__ scratch_near, Counters * __restrict__ cnt, unsigned long long * __restrict__ d_err)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     GravSmem & sm = reinterpret_cast<GravSmem *>(s_dyn)[w];
     // per-lane queue of opened leaves {first, count} and of their softened-pair masks: deep enough that
     // the lanes' particle-particle work evens out before a flush; lives in this warp's scratch slot
-    int2 * const lq = scratch_lq + ((size_t)(blockIdx.x * (blockDim.x >> 5) + w) * GRAV_LQ) * 32 + lane;
-    unsigned * const nearq = scratch_near + ((size_t)(blockIdx.x * (blockDim.x >> 5) + w) * GRAV_LQ) * 32 + lane;
+    // entry = {{first, count}, softening threshold max(h_i, h_leaf)^2}
+    double2 * const lq = scratch_lq + ((size_t)(blockIdx.x * (blockDim.x >> 5) + w) * GRAV_LQ) * 32 + lane;
+    int * const nearq = scratch_near + ((size_t)(blockIdx.x * (blockDim.x >> 5) + w) * GRAV_NEAR) * 32 + lane;
     const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned long long tot_pp = 0, tot_pc = 0, tot_visit = 0;
+    unsigned long long tot_pp = 0, tot_pc = 0, tot_visit = 0, tot_pcg = 0, tot_ppg = 0;
     int g_first, g_cnt;
     while (next_group(gt, lane, g_first, g_cnt)) {
     const int i = g_first + lane;
@@ -802,7 +806,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     }
     const double einv_i = 2.0 / h_i;
     const double h_i2 = h_i * h_i * (1.0 + 1e-12);   // near test: r2 < max(h_i, h_j)^2 with a margin
-    unsigned int n_pp = 0, n_pc = 0, n_visit = 0;             // per lane: fit 32 bits
+    unsigned int n_pp = 0, n_pc = 0, n_visit = 0, n_pcg = 0, n_ppg = 0;   // per lane: fit 32 bits
     unsigned pcw[GV_NB];                                     // lane's accept bits over the blocks of the chunk
 #pragma unroll
     for (int b = 0; b < GV_NB; ++b) pcw[b] = 0;
@@ -847,73 +851,76 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         __syncwarp();
     };
     // queued leaves: particle-particle sums of src/bhtree.cpp:309-317.  Pass 1 runs one flattened
-    // loop over all particles of the lane's queued leaves with the unsoftened form (u >= 2 for both
-    // h_i and h_j, i.e. r >= max(h_i, h_j)) and only MARKS the softened pairs; pass 2 runs the full
-    // Hernquist-Katz form over the marked pairs.  Both bodies run convergent across lanes.
+    // loop over all particles of the lane's queued leaves, two pairs in flight, with the unsoftened
+    // form and only LISTS the pairs that may be softened (r2 < max(h_i, h_leaf)^2 >= max(h_i, h_j)^2:
+    // no per-pair load of h_j); pass 2 runs the full Hernquist-Katz form over the listed pairs (it
+    // reduces to the unsoftened form for u >= 2, so listing too many is harmless).  Both bodies run
+    // convergent across lanes.
+    auto soft_pair = [&](int j) {
+        const double4 pj = ldg4(&posm[j]);
+        const double einv_j = __ldg(&hsoft[j]).x;
+        double d[DIM];
+        rij_from4<DIM>(P, ri, pj, d);
+        const double r2 = dot<DIM>(d, d);
+        const double rinv = rsqrt(r2);              // inf at r == 0, unused there (u < 1 branch)
+        const double r = r2 > 0.0 ? r2 * rinv : 0.0;
+        double fi, gi, fj, gj;
+        soft_fg_fast(r, rinv, einv_i, fi, gi);
+        soft_fg_fast(r, rinv, einv_j, fj, gj);
+        const double gm = P.G * pj.w;
+        phi -= gm * (fi + fj) * 0.5;                // src/bhtree.cpp:314-315
+        const double s = gm * (gi + gj) * 0.5;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
+    };
     auto flush_pp = [&]() {
-        int q = 0, k = 0;
-        int2 cur = make_int2(0, 0);
-        unsigned near = 0;
-        if (nlq > 0) cur = lq[0];
-        while (q < nlq) {
-            const int j = cur.x + k;
-            const double4 pj = ldg4(&posm[j]);
-            const double hj2 = __ldg(&hsoft[j].y);         // h_j^2 (1 + 1e-12)
-            double d[DIM];
-            rij_from4<DIM>(P, ri, pj, d);
-            const double r2 = dot<DIM>(d, d);
-            {
-                // branch-free: a softened ("near") pair contributes 0 here and is marked for pass 2
-                const bool nr = r2 < fmax(h_i2, hj2);
-                near |= (nr ? 1u : 0u) << k;
-                const double rinv = fast_rsqrt(nr ? 1.0 : r2);
-                const double gm = nr ? 0.0 : P.G * pj.w;
-                phi -= gm * rinv;
-                const double s = gm * (rinv * rinv * rinv);
+        int q = 0, j = 0, jend = 0, nnear = 0;
+        double thr2 = 0.0;
+        while (j == jend && q < nlq) {
+            const double2 e = lq[q * 32];
+            ++q;
+            j = __double2loint(e.x); jend = j + __double2hiint(e.x); thr2 = e.y;
+        }
+        while (j < jend) {
+            const bool two = j + 1 < jend;
+            const int j1 = two ? j + 1 : j;
+            const double4 p0 = ldg4(&posm[j]);
+            const double4 p1 = ldg4(&posm[j1]);
+            double d0[DIM], d1[DIM];
+            rij_from4<DIM>(P, ri, p0, d0);
+            rij_from4<DIM>(P, ri, p1, d1);
+            const double r20 = dot<DIM>(d0, d0), r21 = dot<DIM>(d1, d1);
+            // branch-free: a possibly softened pair contributes 0 here and is listed for pass 2
+            const bool n0 = r20 < thr2, n1 = two && r21 < thr2;
+            const double y0 = fast_rsqrt(n0 ? 1.0 : r20), y1 = fast_rsqrt(r21 < thr2 ? 1.0 : r21);
+            const double gm0 = n0 ? 0.0 : P.G * p0.w, gm1 = (!two || r21 < thr2) ? 0.0 : P.G * p1.w;
+            phi -= gm0 * y0;
+            phi -= gm1 * y1;
+            const double s0 = gm0 * y0 * (y0 * y0), s1 = gm1 * y1 * (y1 * y1);
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
-            }
-            if (++k == cur.y) {
-                n_pp += k;
-                nearq[q * 32] = near;
-                near = 0;
-                k = 0;
-                ++q;
-                if (q < nlq) cur = lq[q * 32];
+            for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
+            if (n0) { if (nnear < GRAV_NEAR) { nearq[nnear * 32] = j; ++nnear; } else soft_pair(j); }
+            if (n1) { if (nnear < GRAV_NEAR) { nearq[nnear * 32] = j1; ++nnear; } else soft_pair(j1); }
+            n_pp += two ? 2 : 1;
+            j += 2;
+            if (j >= jend) {
+                j = jend;
+                while (j == jend && q < nlq) {
+                    const double2 e = lq[q * 32];
+                    ++q;
+                    j = __double2loint(e.x); jend = j + __double2hiint(e.x); thr2 = e.y;
+                }
             }
         }
-        q = 0;
-        near = 0;
-        int first = 0;
-        for (;;) {
-            while (near == 0 && q < nlq) { near = nearq[q * 32]; first = lq[q * 32].x; ++q; }
-            if (near == 0) break;
-            const int j = first + __ffs(near) - 1;
-            near &= near - 1;
-            const double4 pj = ldg4(&posm[j]);
-            const double einv_j = __ldg(&hsoft[j]).x;
-            double d[DIM];
-            rij_from4<DIM>(P, ri, pj, d);
-            const double r2 = dot<DIM>(d, d);
-            const double rinv = rsqrt(r2);              // inf at r == 0, unused there (u < 1 branch)
-            const double r = r2 > 0.0 ? r2 * rinv : 0.0;
-            double fi, gi, fj, gj;
-            soft_fg_fast(r, rinv, einv_i, fi, gi);
-            soft_fg_fast(r, rinv, einv_j, fj, gj);
-            const double gm = P.G * pj.w;
-            phi -= gm * (fi + fj) * 0.5;                // src/bhtree.cpp:314-315
-            const double s = gm * (gi + gj) * 0.5;
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
-        }
+        for (int k = 0; k < nnear; ++k) soft_pair(nearq[k * 32]);
         nlq = 0;
     };
     // lanes with `me` queue the leaf [first, first + count) in 32-particle pieces (leaves deeper than
-    // 32 particles exist at the maximum tree level)
-    auto queue_leaf = [&](bool me, int first, int count) {
+    // 32 particles exist at the maximum tree level); hl2 = largest h^2 in the leaf
+    auto queue_leaf = [&](bool me, int first, int count, double hl2) {
         const int last = first + count;
         for (int base = first; base < last; base += 32) {
-            if (me) { lq[nlq * 32] = make_int2(base, min(32, last - base)); ++nlq; }
+            if (me) { lq[nlq * 32] = make_double2(pack_ints(base, min(32, last - base)), fmax(h_i2, hl2)); ++nlq; }
             if (__any_sync(SPHB_FULL_MASK, nlq == GRAV_LQ)) flush_pp();
         }
     };
@@ -969,7 +976,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         }
         // ---- classify the batch against the group's bounding box
         int cls = 0, child0 = 0, nchild = 0, first = 0, count = 0;
-        double c[DIM], e2 = 0.0, mass = 0.0;
+        double c[DIM], e2 = 0.0, mass = 0.0, hl2 = 0.0;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) c[d] = 0.0;
         if (node >= 0) {
@@ -996,10 +1003,15 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             if (nchild == 0 && cls != 1) {
                 const double2 q3 = __ldg(t.ng + (size_t)node * 4 + 3);
                 first = __double2loint(q3.x); count = __double2hiint(q3.x);
+                hl2 = q3.y;
             }
         }
         if (cnt) {
             for (int s = 0; s < k; ++s) n_visit += (__shfl_sync(SPHB_FULL_MASK, mask, s) >> lane) & 1u;
+            const unsigned bf = __ballot_sync(SPHB_FULL_MASK, cls == 1 && mask == vmask);
+            if (valid) n_pcg += __popc(bf);
+            unsigned lf = __ballot_sync(SPHB_FULL_MASK, cls == 2 && nchild == 0 && mask == vmask);
+            while (lf) { const int src = __ffs(lf) - 1; lf &= lf - 1; const int c0 = __shfl_sync(SPHB_FULL_MASK, count, src); if (valid) n_ppg += c0; }
         }
         const unsigned b_acc = __ballot_sync(SPHB_FULL_MASK, cls == 1);
         const unsigned b_mix = __ballot_sync(SPHB_FULL_MASK, cls == 3);
@@ -1024,6 +1036,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             sm.mx[slot] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, mass);
             sm.me2[slot] = e2;
             sm.minfo[slot] = make_int4(child0, nchild, first, count);
+            sm.mh2[slot] = hl2;
             sm.mmask[slot] = mask;
         }
         // (c) cells somebody accepts (class 1: every lane of the mask; class 3: decided below) get the
@@ -1046,7 +1059,8 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 const int f0 = __shfl_sync(SPHB_FULL_MASK, first, src);
                 const int c0 = __shfl_sync(SPHB_FULL_MASK, count, src);
                 const unsigned m = __shfl_sync(SPHB_FULL_MASK, mask, src);
-                queue_leaf((m >> lane) & 1u, f0, c0);
+                const double l2 = __shfl_sync(SPHB_FULL_MASK, hl2, src);
+                queue_leaf((m >> lane) & 1u, f0, c0, l2);
             }
         }
         // ---- fetch the next batch now: its loads are in flight during the per-lane tests
@@ -1072,7 +1086,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             if (cls == 3 && mslot == q) racc = a_b;        // the node's own lane keeps its accept mask
             if (o_b) {
                 if (info.y == 0) {
-                    queue_leaf(open, info.z, info.w);
+                    queue_leaf(open, info.z, info.w, sm.mh2[q]);
                 } else if (top + 1 > GV_STACK) {
                     if (lane == 0) atomicOr(&d_err[2], (unsigned long long)WALK_ERR_GRAV_STACK);
                 } else {
@@ -1097,13 +1111,15 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
 #pragma unroll
         for (int a = 0; a < DIM; ++a) p.acc[a][i] = acc[a];
         p.phi[i] = phi;
-        tot_pp += n_pp; tot_pc += n_pc; tot_visit += n_visit;
+        tot_pp += n_pp; tot_pc += n_pc; tot_visit += n_visit; tot_pcg += n_pcg; tot_ppg += n_ppg;
     }
     __syncwarp();
     }
     if (cnt) {
         const unsigned long long a = warp_sum_u64(tot_pp), b = warp_sum_u64(tot_pc), cc = warp_sum_u64(tot_visit);
-        if (lane == 0) { atomicAdd(&cnt->grav_pp, a); atomicAdd(&cnt->grav_pc, b); atomicAdd(&cnt->grav_node_visits, cc); }
+        const unsigned long long pg = warp_sum_u64(tot_pcg), qg = warp_sum_u64(tot_ppg);
+        if (lane == 0) { atomicAdd(&cnt->grav_pp, a); atomicAdd(&cnt->grav_pc, b); atomicAdd(&cnt->grav_node_visits, cc);
+                         atomicAdd(&cnt->grav_pc_group, pg); atomicAdd(&cnt->grav_pp_group, qg); }
     }
 }
 
@@ -1114,6 +1130,21 @@ __global__ void k_grav_pack(const double * __restrict__ sml, double2 * __restric
     if (i >= n) return;
     const double h = sml[i];
     hsoft[i] = make_double2(2.0 / h, h * h * (1.0 + 1e-12));
+}
+
+// per leaf: the largest h^2 (with the margin of hsoft.y) among its particles -> ng record [3].y, the
+// softening threshold of the particle-particle pass 1
+__global__ void k_grav_leaf_h(TreeDev t, const double * __restrict__ sml)
+{
+    const int D = blockIdx.x * blockDim.x + threadIdx.x;
+    if (D >= t.n_nodes) return;
+    double2 * ng = t.ng + (size_t)D * 4;
+    const double2 q2 = ng[2], q3 = ng[3];
+    if (__double2hiint(q2.y)) return;                  // internal node
+    const int first = __double2loint(q3.x), count = __double2hiint(q3.x);
+    double h = 0.0;
+    for (int j = first; j < first + count; ++j) h = fmax(h, sml[j]);
+    ng[3].y = h * h * (1.0 + 1e-12);
 }
 
 // Direct sum, the EXHAUSTIVE_SEARCH flavour of GravityForce (src/gravity_force.cpp:70-84).

@@ -46,7 +46,8 @@ class SphbParams(C.Structure):
 class SphbCounters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in (
         "n_particles", "newton_evals", "newton_iters", "pre_candidates", "pre_neighbors", "force_pairs",
-        "grav_pp", "grav_pc", "grav_node_visits", "tree_nodes", "tree_leaves")]
+        "grav_pp", "grav_pc", "grav_node_visits", "tree_nodes", "tree_leaves",
+        "grav_pc_group", "grav_pp_group", "n_groups")]
 
 
 _SPH = {"ssph": 0, "disph": 1, "gsph": 2}
