@@ -15,6 +15,9 @@ for r in rows:
     elif r[0] == "Line No":
         hdr = r
     elif hdr and r[0].isdigit():
+        if len(r) > len(hdr):                      # source text with unescaped quotes / commas
+            extra = len(r) - len(hdr)
+            r = [r[0], ",".join(r[1:2 + extra])] + r[2 + extra:]
         d = dict(zip(hdr, [x if x not in ("-", "") else "0" for x in r]))
         # two "Source" columns: first is the CUDA line
         lines.append((fname, int(r[0]), r[1].strip(), int(d.get("# Samples", 0) or 0), int(d.get("Instructions Executed", 0) or 0),

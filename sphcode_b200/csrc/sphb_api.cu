@@ -214,7 +214,7 @@ int alloc_particles(sphb_ctx * c, int n)
 
     // list scratch: one r, j (and m) column set per resident warp of the persistent pre / force kernels
     c->pre_grid = std::min(cdiv(groups, 4), c->sm_count * 5);       // pre / force: 5 resident blocks per SM
-    c->grav_grid = std::min(cdiv(groups, 4), c->sm_count * 4);      // gravity: 4
+    c->grav_grid = std::min(cdiv(groups, 4), c->sm_count * GV_BLOCKS);
     const size_t slots = (size_t)c->pre_grid * 4;
     if (dev_alloc(c, &c->scratch_r, slots * c->P.list_cap * 32, c->allocs)) return 1;
     if (dev_alloc(c, &c->scratch_j, slots * c->P.list_cap * 32, c->allocs)) return 1;
@@ -567,9 +567,15 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
         k_grav_leaf_h<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td, c->cur.sml); LAUNCH_CHECK();
         GroupTable gt;
         if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
-        static bool attr_set = false;
-        if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(GravSmem)))); attr_set = true; }
-        k_gravity<DIM><<<c->grav_grid, 128, 4 * sizeof(GravSmem), c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, c->grav_lq, c->grav_near, c->counters_on ? c->d_cnt : nullptr, c->d_err);
+        const int smem = (int)(4 * sizeof(GravSmem));
+#define SPHB_GRAV(PER, CNT) do { \
+            static bool attr_set = false; \
+            if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity<DIM, PER, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; } \
+            k_gravity<DIM, PER, CNT><<<c->grav_grid, 128, smem, c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, \
+                c->grav_lq, c->grav_near, c->d_cnt, c->d_err); } while (0)
+        if (c->P.periodic) { if (c->counters_on) SPHB_GRAV(true, true); else SPHB_GRAV(true, false); }
+        else               { if (c->counters_on) SPHB_GRAV(false, true); else SPHB_GRAV(false, false); }
+#undef SPHB_GRAV
         LAUNCH_CHECK();
     }
     return 0;

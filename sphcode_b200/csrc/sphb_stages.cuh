@@ -740,21 +740,39 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 //   * opened leaves go to a per-lane queue of (first, count); when any lane's queue is full, every
 //     lane runs one flattened loop over all particles of its queued leaves (packed x,y,z,m + 2/h
 //     read through L1; lanes of a warp are Morton neighbours and share these lines).
-constexpr int GRAV_LQ = 64;       // leaf queue depth per lane (global scratch, [entry][lane])
+#ifndef SPHB_GRAV_LQ
+#define SPHB_GRAV_LQ 96
+#endif
+#ifndef SPHB_GV_BLOCKS
+#define SPHB_GV_BLOCKS 4
+#endif
+#ifndef SPHB_GV_GC
+#define SPHB_GV_GC 64
+#endif
+#ifndef SPHB_GV_GROUPCELLS
+#define SPHB_GV_GROUPCELLS 1
+#endif
+constexpr int GV_BLOCKS = SPHB_GV_BLOCKS;   // resident blocks per SM of k_gravity
+constexpr int GRAV_LQ = SPHB_GRAV_LQ;       // leaf queue depth per lane (global scratch, [entry][lane])
 constexpr int GRAV_NEAR = 128;    // softened-pair list depth per lane (global scratch, [entry][lane])
-constexpr int GV_STACK = 704;     // node stack entries per warp (<= 28 stay behind per tree level, see pop_load)
-constexpr int GV_NB = 2;          // batches of accepted cells per chunk
-constexpr int GV_PC = 32 * GV_NB; // chunk slots: slot = 32 * block + lane of the node in its batch
+#ifndef SPHB_GV_STACK
+#define SPHB_GV_STACK 704
+#endif
+constexpr int GV_STACK = SPHB_GV_STACK;     // node stack entries per warp (<= 28 stay behind per tree level, see pop_load)
+constexpr int GV_NB = 2;          // 32-bit words of a lane's accept mask over the chunk
+constexpr int GV_PC = 32 * GV_NB; // chunk slots, filled densely; flushed when another batch might not fit
+constexpr int GV_GC = SPHB_GV_GC; // list of cells accepted by the whole group, flushed likewise
 
 struct GravSmem {
     int2     stack[GV_STACK];           // {child0 | (nchild - 1) << 29, lane mask}: the children of an opened node
     int2     expand[32];                // {node, lane mask} of the batch being fetched
     double   pcx[GV_PC], pcy[GV_PC], pcz[GV_PC], pcm[GV_PC];   // accepted cells of the current chunk: mass centre, G * mass
+    double4  gcell[GV_GC + 1];          // cells accepted by EVERY particle of the group: mass centre, G * mass (+ pad)
     double4  mx[32];                    // mixed nodes of the current batch: mass centre + mass
     double   me2[32];                   //   edge^2
     int4     minfo[32];                 //   {child0, nchild, first, count}
     double   mh2[32];                   //   leaves: largest h^2 among the leaf's particles (k_grav_leaf_h)
-    unsigned mmask[32];                 //   lane mask
+    unsigned mmask[32];                 //   lane mask; afterwards the accept rows of the batch, compacted
 };
 
 // Softening functions with the divisions by constants turned into products (soft_fg in
@@ -776,8 +794,26 @@ __device__ __forceinline__ void soft_fg_fast(double r, double rinv, double einv,
     }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(128, 4)
+// r_i - c with the minimum image folded in at compile time
+template <int DIM, bool PERIODIC>
+__device__ __forceinline__ void grav_rij(const DevParams & P, const double (&ri)[DIM], const double4 & pj, double (&d)[DIM])
+{
+    d[0] = ri[0] - pj.x;
+    if (DIM >= 2) d[DIM >= 2 ? 1 : 0] = ri[DIM >= 2 ? 1 : 0] - pj.y;
+    if (DIM >= 3) d[DIM >= 3 ? 2 : 0] = ri[DIM >= 3 ? 2 : 0] - pj.z;
+    if (PERIODIC) {
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) d[a] = min_image(d[a], P.range[a]);
+    }
+}
+
+// Code size matters here: the SM's instruction cache holds 32 KB, the warps of an SM sit in different
+// phases of this kernel, and instruction fetch from L2 showed up as the top stall as soon as the
+// interaction loops were inlined at several call sites.  Hence every interaction loop exists ONCE
+// (all flushes happen at the head of the walk loop), PERIODIC and COUNT are compile-time, and the
+// counters are a separate instantiation.
+template <int DIM, bool PERIODIC, bool COUNT>
+__global__ void __launch_bounds__(128, GV_BLOCKS)
 k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restrict__ posm,
           const double2 * __restrict__ hsoft /* {2/h_j, h_j^2} */, double2 * __restrict__ scratch_lq,
           int * __restrict__ scratch_near, Counters * __restrict__ cnt, unsigned long long * __restrict__ d_err)
@@ -785,9 +821,9 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     extern __shared__ __align__(16) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     GravSmem & sm = reinterpret_cast<GravSmem *>(s_dyn)[w];
-    // per-lane queue of opened leaves {first, count} and of their softened-pair masks: deep enough that
-    // the lanes' particle-particle work evens out before a flush; lives in this warp's scratch slot
-    // entry = {{first, count}, softening threshold max(h_i, h_leaf)^2}
+    // per-lane queue of opened leaves, entry = {{first, count}, softening threshold max(h_i, h_leaf)^2},
+    // deep enough that the lanes' particle-particle work evens out before a flush, and per-lane list of
+    // possibly softened pairs; both live in this warp's global scratch slot, [entry][lane]
     double2 * const lq = scratch_lq + ((size_t)(blockIdx.x * (blockDim.x >> 5) + w) * GRAV_LQ) * 32 + lane;
     int * const nearq = scratch_near + ((size_t)(blockIdx.x * (blockDim.x >> 5) + w) * GRAV_NEAR) * 32 + lane;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -805,125 +841,17 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         h_i = p.sml[i];
     }
     const double einv_i = 2.0 / h_i;
-    const double h_i2 = h_i * h_i * (1.0 + 1e-12);   // near test: r2 < max(h_i, h_j)^2 with a margin
+    const double h_i2 = h_i * h_i * (1.0 + 1e-12);           // softening test: r2 < max(h_i, h_j)^2 with a margin
     unsigned int n_pp = 0, n_pc = 0, n_visit = 0, n_pcg = 0, n_ppg = 0;   // per lane: fit 32 bits
-    unsigned pcw[GV_NB];                                     // lane's accept bits over the blocks of the chunk
-#pragma unroll
-    for (int b = 0; b < GV_NB; ++b) pcw[b] = 0;
-    int npb = 0, nlq = 0;                                    // blocks in use
+    unsigned pcw0 = 0, pcw1 = 0;                             // lane's accept bits over the chunk slots
+    int npb = 0, nlq = 0, ngc = 0;                           // chunk slots, leaf queue entries, group cells in use
 
     double bc[DIM], bh[DIM];
     group_box<DIM>(ri, valid, bc, bh);
     const unsigned vmask = __ballot_sync(SPHB_FULL_MASK, valid);
-
-    // accepted cells of the current chunk: monopole, src/bhtree.cpp:326-330; two cells in flight
-    auto flush_pc = [&]() {
-        __syncwarp();
+    double cmax = 0.0;
 #pragma unroll
-        for (int blk = 0; blk < GV_NB; ++blk) {
-            unsigned mm = pcw[blk];
-            n_pc += __popc(mm);
-            const double * px = sm.pcx + blk * 32, * py = sm.pcy + blk * 32, * pz = sm.pcz + blk * 32, * pm = sm.pcm + blk * 32;
-            while (mm) {
-                const int e0 = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const bool two = mm != 0;
-                const int e1 = two ? __ffs(mm) - 1 : e0;
-                mm &= mm - 1;                                  // stays 0 when !two
-                double c0[DIM], c1[DIM], d0[DIM], d1[DIM];
-                c0[0] = px[e0]; c1[0] = px[e1];
-                if (DIM >= 2) { c0[DIM >= 2 ? 1 : 0] = py[e0]; c1[DIM >= 2 ? 1 : 0] = py[e1]; }
-                if (DIM >= 3) { c0[DIM >= 3 ? 2 : 0] = pz[e0]; c1[DIM >= 3 ? 2 : 0] = pz[e1]; }
-                const double gm0 = pm[e0], gm1 = two ? pm[e1] : 0.0;
-                calc_r_ij<DIM>(P, ri, c0, d0);
-                calc_r_ij<DIM>(P, ri, c1, d1);
-                const double ri0 = fast_rsqrt(dot<DIM>(d0, d0)), ri1 = fast_rsqrt(dot<DIM>(d1, d1));
-                phi -= gm0 * ri0;
-                phi -= gm1 * ri1;
-                const double s0 = gm0 * ri0 * (ri0 * ri0), s1 = gm1 * ri1 * (ri1 * ri1);
-#pragma unroll
-                for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < GV_NB; ++b) pcw[b] = 0;
-        npb = 0;
-        __syncwarp();
-    };
-    // queued leaves: particle-particle sums of src/bhtree.cpp:309-317.  Pass 1 runs one flattened
-    // loop over all particles of the lane's queued leaves, two pairs in flight, with the unsoftened
-    // form and only LISTS the pairs that may be softened (r2 < max(h_i, h_leaf)^2 >= max(h_i, h_j)^2:
-    // no per-pair load of h_j); pass 2 runs the full Hernquist-Katz form over the listed pairs (it
-    // reduces to the unsoftened form for u >= 2, so listing too many is harmless).  Both bodies run
-    // convergent across lanes.
-    auto soft_pair = [&](int j) {
-        const double4 pj = ldg4(&posm[j]);
-        const double einv_j = __ldg(&hsoft[j]).x;
-        double d[DIM];
-        rij_from4<DIM>(P, ri, pj, d);
-        const double r2 = dot<DIM>(d, d);
-        const double rinv = rsqrt(r2);              // inf at r == 0, unused there (u < 1 branch)
-        const double r = r2 > 0.0 ? r2 * rinv : 0.0;
-        double fi, gi, fj, gj;
-        soft_fg_fast(r, rinv, einv_i, fi, gi);
-        soft_fg_fast(r, rinv, einv_j, fj, gj);
-        const double gm = P.G * pj.w;
-        phi -= gm * (fi + fj) * 0.5;                // src/bhtree.cpp:314-315
-        const double s = gm * (gi + gj) * 0.5;
-#pragma unroll
-        for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
-    };
-    auto flush_pp = [&]() {
-        int q = 0, j = 0, jend = 0, nnear = 0;
-        double thr2 = 0.0;
-        while (j == jend && q < nlq) {
-            const double2 e = lq[q * 32];
-            ++q;
-            j = __double2loint(e.x); jend = j + __double2hiint(e.x); thr2 = e.y;
-        }
-        while (j < jend) {
-            const bool two = j + 1 < jend;
-            const int j1 = two ? j + 1 : j;
-            const double4 p0 = ldg4(&posm[j]);
-            const double4 p1 = ldg4(&posm[j1]);
-            double d0[DIM], d1[DIM];
-            rij_from4<DIM>(P, ri, p0, d0);
-            rij_from4<DIM>(P, ri, p1, d1);
-            const double r20 = dot<DIM>(d0, d0), r21 = dot<DIM>(d1, d1);
-            // branch-free: a possibly softened pair contributes 0 here and is listed for pass 2
-            const bool n0 = r20 < thr2, n1 = two && r21 < thr2;
-            const double y0 = fast_rsqrt(n0 ? 1.0 : r20), y1 = fast_rsqrt(r21 < thr2 ? 1.0 : r21);
-            const double gm0 = n0 ? 0.0 : P.G * p0.w, gm1 = (!two || r21 < thr2) ? 0.0 : P.G * p1.w;
-            phi -= gm0 * y0;
-            phi -= gm1 * y1;
-            const double s0 = gm0 * y0 * (y0 * y0), s1 = gm1 * y1 * (y1 * y1);
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
-            if (n0) { if (nnear < GRAV_NEAR) { nearq[nnear * 32] = j; ++nnear; } else soft_pair(j); }
-            if (n1) { if (nnear < GRAV_NEAR) { nearq[nnear * 32] = j1; ++nnear; } else soft_pair(j1); }
-            n_pp += two ? 2 : 1;
-            j += 2;
-            if (j >= jend) {
-                j = jend;
-                while (j == jend && q < nlq) {
-                    const double2 e = lq[q * 32];
-                    ++q;
-                    j = __double2loint(e.x); jend = j + __double2hiint(e.x); thr2 = e.y;
-                }
-            }
-        }
-        for (int k = 0; k < nnear; ++k) soft_pair(nearq[k * 32]);
-        nlq = 0;
-    };
-    // lanes with `me` queue the leaf [first, first + count) in 32-particle pieces (leaves deeper than
-    // 32 particles exist at the maximum tree level); hl2 = largest h^2 in the leaf
-    auto queue_leaf = [&](bool me, int first, int count, double hl2) {
-        const int last = first + count;
-        for (int base = first; base < last; base += 32) {
-            if (me) { lq[nlq * 32] = make_double2(pack_ints(base, min(32, last - base)), fmax(h_i2, hl2)); ++nlq; }
-            if (__any_sync(SPHB_FULL_MASK, nlq == GRAV_LQ)) flush_pp();
-        }
-    };
+    for (int d = 0; d < DIM; ++d) cmax = fmax(cmax, fabs(bc[d]) + bh[d]);
 
     // ---- node stack and the batch held in registers.  A stack entry stands for ALL children of an
     // opened node (they are contiguous), so a batch of <= 32 nodes pushes <= 32 entries and pops >= 32 / NCH:
@@ -934,47 +862,136 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     int k = 0, node = -1;
     unsigned mask = 0;
     double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0;
-    auto pop_load = [&]() {
-        const int ne = min(top, 32);
-        int2 ent = make_int2(0, 0);
-        int nc = 0;
-        if (lane < ne) { ent = sm.stack[top - 1 - lane]; nc = (int)((unsigned)ent.x >> 29) + 1; }
-        int incl = nc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(SPHB_FULL_MASK, incl, o);
-            if (lane >= o) incl += y;
-        }
-        const int m = __popc(__ballot_sync(SPHB_FULL_MASK, lane < ne && incl <= 32));   // entries taken (a prefix)
-        k = m > 0 ? __shfl_sync(SPHB_FULL_MASK, incl, m - 1) : 0;
-        if (lane < m) {
-            const int c0 = ent.x & 0x1fffffff;
-            for (int ci = 0; ci < nc; ++ci) sm.expand[incl - nc + ci] = make_int2(c0 + ci, ent.y);
-        }
-        __syncwarp();
-        node = -1;
-        mask = 0;
-        if (lane < k) {
-            const int2 e = sm.expand[lane];
-            node = e.x;
-            mask = (unsigned)e.y;
-            const double2 * q = t.ng + (size_t)node * 4;
-            q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2);
-        }
-        top -= m;
-        __syncwarp();
-    };
-    double cmax = 0.0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) cmax = fmax(cmax, fabs(bc[d]) + bh[d]);
 
-    pop_load();
     for (;;) {
-        if (k == 0) {
-            if (top == 0) break;
-            pop_load();
+        const bool last = (k == 0 && top == 0);
+        // ================= interaction loops (each exists once; all lanes arrive together) =================
+        // (1) queued leaves: particle-particle sums of src/bhtree.cpp:309-317.  Pass 1 runs one flattened
+        // loop over all particles of the lane's queued leaves, two pairs in flight, with the unsoftened
+        // form and only LISTS the pairs that may be softened (r2 < max(h_i, h_leaf)^2 >= max(h_i, h_j)^2:
+        // no per-pair load of h_j); pass 2 runs the full Hernquist-Katz form over the listed pairs (it
+        // reduces to the unsoftened form for u >= 2, so listing too many is harmless).
+        if (last || __any_sync(SPHB_FULL_MASK, nlq > GRAV_LQ - 32)) {
+            int q = 0, j = 0, jend = 0;
+            double thr2 = 0.0;
+            double2 en = make_double2(0.0, 0.0);           // the entry after the current one, already loaded
+            if (nlq > 0) {
+                const double2 e = lq[0];
+                j = __double2loint(e.x); jend = j + __double2hiint(e.x); thr2 = e.y;
+                q = 1;
+                if (nlq > 1) en = lq[32];
+            }
+            do {
+                int nnear = 0;
+                while (j < jend && nnear <= GRAV_NEAR - 2) {
+                    const bool two = j + 1 < jend;
+                    const int j1 = two ? j + 1 : j;
+                    const double4 p0 = ldg4(&posm[j]);
+                    const double4 p1 = ldg4(&posm[j1]);
+                    double d0[DIM], d1[DIM];
+                    grav_rij<DIM, PERIODIC>(P, ri, p0, d0);
+                    grav_rij<DIM, PERIODIC>(P, ri, p1, d1);
+                    const double r20 = dot<DIM>(d0, d0), r21 = dot<DIM>(d1, d1);
+                    // branch-free: a possibly softened pair contributes 0 here and is listed for pass 2
+                    const bool n0 = r20 < thr2, n1x = r21 < thr2, n1 = two && n1x;
+                    const double y0 = fast_rsqrt(n0 ? 1.0 : r20), y1 = fast_rsqrt(n1x ? 1.0 : r21);
+                    const double gm0 = n0 ? 0.0 : P.G * p0.w, gm1 = (!two || n1x) ? 0.0 : P.G * p1.w;
+                    phi -= gm0 * y0;
+                    phi -= gm1 * y1;
+                    const double s0 = gm0 * y0 * (y0 * y0), s1 = gm1 * y1 * (y1 * y1);
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
+                    if (n0) { nearq[nnear * 32] = j; ++nnear; }
+                    if (n1) { nearq[nnear * 32] = j1; ++nnear; }
+                    if (COUNT) n_pp += two ? 2 : 1;
+                    j += 2;
+                    if (j >= jend) {                            // next leaf: its entry is in registers already
+                        const bool more = q < nlq;
+                        j = more ? __double2loint(en.x) : 0;
+                        jend = more ? j + __double2hiint(en.x) : 0;
+                        thr2 = en.y;
+                        ++q;
+                        if (q < nlq) en = lq[q * 32];
+                    }
+                }
+                for (int kk = 0; kk < nnear; ++kk) {
+                    const int jn = nearq[kk * 32];
+                    const double4 pj = ldg4(&posm[jn]);
+                    const double einv_j = __ldg(&hsoft[jn]).x;
+                    double d[DIM];
+                    grav_rij<DIM, PERIODIC>(P, ri, pj, d);
+                    const double r2 = dot<DIM>(d, d);
+                    const double rinv = rsqrt(r2);              // inf at r == 0, unused there (u < 1 branch)
+                    const double r = r2 > 0.0 ? r2 * rinv : 0.0;
+                    double fi, gi, fj, gj;
+                    soft_fg_fast(r, rinv, einv_i, fi, gi);
+                    soft_fg_fast(r, rinv, einv_j, fj, gj);
+                    const double gm = P.G * pj.w;
+                    phi -= gm * (fi + fj) * 0.5;                // src/bhtree.cpp:314-315
+                    const double s = gm * (gi + gj) * 0.5;
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
+                }
+            } while (j < jend);                                 // only if the softened-pair list ran full
+            nlq = 0;
         }
-        // ---- classify the batch against the group's bounding box
+        // (2) accepted cells of the chunk (monopole, src/bhtree.cpp:326-330): every lane runs over ITS
+        // accept bits, two cells in flight
+        if (last || npb > GV_PC - 32) {
+            __syncwarp();
+            if (COUNT) n_pc += __popc(pcw0) + __popc(pcw1);
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                unsigned mm = blk == 0 ? pcw0 : pcw1;
+                const double * px = sm.pcx + blk * 32, * py = sm.pcy + blk * 32, * pz = sm.pcz + blk * 32, * pm = sm.pcm + blk * 32;
+                while (mm) {
+                    const int e0 = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const bool two = mm != 0;
+                    const int e1 = two ? __ffs(mm) - 1 : e0;
+                    mm &= mm - 1;                                  // stays 0 when !two
+                    const double4 c0 = make_double4(px[e0], DIM >= 2 ? py[e0] : 0.0, DIM >= 3 ? pz[e0] : 0.0, pm[e0]);
+                    const double4 c1 = make_double4(px[e1], DIM >= 2 ? py[e1] : 0.0, DIM >= 3 ? pz[e1] : 0.0, two ? pm[e1] : 0.0);
+                    double d0[DIM], d1[DIM];
+                    grav_rij<DIM, PERIODIC>(P, ri, c0, d0);
+                    grav_rij<DIM, PERIODIC>(P, ri, c1, d1);
+                    const double y0 = fast_rsqrt(dot<DIM>(d0, d0)), y1 = fast_rsqrt(dot<DIM>(d1, d1));
+                    phi -= c0.w * y0;
+                    phi -= c1.w * y1;
+                    const double s0 = c0.w * y0 * (y0 * y0), s1 = c1.w * y1 * (y1 * y1);
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
+                }
+            }
+            pcw0 = 0; pcw1 = 0;
+            npb = 0;
+            __syncwarp();
+        }
+        // (3) cells accepted by every particle of the group: all lanes run the same loop over the list,
+        // broadcast reads, two cells in flight
+        if (last || ngc > GV_GC - 32) {
+            __syncwarp();
+            if (COUNT) n_pc += ngc;
+            if (ngc & 1) { if (lane == 0) sm.gcell[ngc] = make_double4(1e30, 1e30, 1e30, 0.0); ++ngc; }   // pad to even with a massless cell
+            __syncwarp();
+            for (int kk = 0; kk < ngc; kk += 2) {
+                const double4 c0 = sm.gcell[kk], c1 = sm.gcell[kk + 1];
+                double d0[DIM], d1[DIM];
+                grav_rij<DIM, PERIODIC>(P, ri, c0, d0);
+                grav_rij<DIM, PERIODIC>(P, ri, c1, d1);
+                const double y0 = fast_rsqrt(dot<DIM>(d0, d0)), y1 = fast_rsqrt(dot<DIM>(d1, d1));
+                phi -= c0.w * y0;
+                phi -= c1.w * y1;
+                const double s0 = c0.w * y0 * (y0 * y0), s1 = c1.w * y1 * (y1 * y1);
+#pragma unroll
+                for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
+            }
+            ngc = 0;
+            __syncwarp();
+        }
+        if (last) break;
+
+        // ================= the walk: classify the batch against the group's bounding box =================
         int cls = 0, child0 = 0, nchild = 0, first = 0, count = 0;
         double c[DIM], e2 = 0.0, mass = 0.0, hl2 = 0.0;
 #pragma unroll
@@ -991,7 +1008,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             for (int d = 0; d < DIM; ++d) {
                 const double slack = 1e-13 * (cmax + fabs(c[d])) + 1e-300;
                 double dc = bc[d] - c[d];
-                if (P.periodic) dc = min_image(dc, P.range[d]);
+                if (PERIODIC) dc = min_image(dc, P.range[d]);
                 dc = fabs(dc);
                 const double lo = fmax(dc - bh[d] - slack, 0.0), hi = dc + bh[d] + slack;
                 dmin2 += lo * lo;
@@ -1006,14 +1023,16 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 hl2 = q3.y;
             }
         }
-        if (cnt) {
+        if (COUNT) {
             for (int s = 0; s < k; ++s) n_visit += (__shfl_sync(SPHB_FULL_MASK, mask, s) >> lane) & 1u;
             const unsigned bf = __ballot_sync(SPHB_FULL_MASK, cls == 1 && mask == vmask);
             if (valid) n_pcg += __popc(bf);
             unsigned lf = __ballot_sync(SPHB_FULL_MASK, cls == 2 && nchild == 0 && mask == vmask);
             while (lf) { const int src = __ffs(lf) - 1; lf &= lf - 1; const int c0 = __shfl_sync(SPHB_FULL_MASK, count, src); if (valid) n_ppg += c0; }
         }
-        const unsigned b_acc = __ballot_sync(SPHB_FULL_MASK, cls == 1);
+        const bool grp = SPHB_GV_GROUPCELLS && cls == 1 && mask == vmask;      // accepted by the whole group
+        const unsigned b_grp = __ballot_sync(SPHB_FULL_MASK, grp);
+        const unsigned b_acc = __ballot_sync(SPHB_FULL_MASK, cls == 1 && !grp);
         const unsigned b_mix = __ballot_sync(SPHB_FULL_MASK, cls == 3);
         const unsigned b_oleaf = __ballot_sync(SPHB_FULL_MASK, cls == 2 && nchild == 0);
         const unsigned b_oint = __ballot_sync(SPHB_FULL_MASK, cls == 2 && nchild > 0);
@@ -1029,28 +1048,33 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 top += total;
             }
         }
-        // (d) mixed nodes -> list in shared memory (tested lane by lane below)
+        // (b) mixed nodes -> list in shared memory (tested lane by lane below)
         const int nmix = __popc(b_mix);
-        if (cls == 3) {
-            const int slot = __popc(b_mix & lt_mask);
-            sm.mx[slot] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, mass);
-            sm.me2[slot] = e2;
-            sm.minfo[slot] = make_int4(child0, nchild, first, count);
-            sm.mh2[slot] = hl2;
-            sm.mmask[slot] = mask;
-        }
-        // (c) cells somebody accepts (class 1: every lane of the mask; class 3: decided below) get the
-        // chunk slot {block npb, this lane}; racc = lanes that accept this lane's node
-        unsigned racc = cls == 1 ? mask : 0u;
         const int mslot = __popc(b_mix & lt_mask);         // class 3: position in the mixed list
-        if (cls == 1 || cls == 3) {
-            const int e = npb * 32 + lane;
+        if (cls == 3) {
+            sm.mx[mslot] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, mass);
+            sm.me2[mslot] = e2;
+            sm.minfo[mslot] = make_int4(child0, nchild, first, count);
+            sm.mh2[mslot] = hl2;
+            sm.mmask[mslot] = mask;
+        }
+        // (c) cells the whole group accepts -> group list
+        if (grp) sm.gcell[ngc + __popc(b_grp & lt_mask)] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, P.G * mass);
+        ngc += __popc(b_grp);
+        // (d) cells some lanes accept (class 1 with a partial mask: every lane of the mask; class 3: decided
+        // below) get the next free chunk slots; racc = lanes that accept this lane's node
+        const unsigned b_sel = b_acc | b_mix;
+        const int sslot = __popc(b_sel & lt_mask);         // position among the batch's chunk cells
+        unsigned racc = (cls == 1 && !grp) ? mask : 0u;
+        if ((cls == 1 && !grp) || cls == 3) {
+            const int e = npb + sslot;
             sm.pcx[e] = c[0];
             if (DIM >= 2) sm.pcy[e] = c[DIM >= 2 ? 1 : 0];
             if (DIM >= 3) sm.pcz[e] = c[DIM >= 3 ? 2 : 0];
             sm.pcm[e] = P.G * mass;
         }
-        // (b) opened by every lane of the mask, leaf -> per-lane queues
+        // (e) opened by every lane of the mask, leaf -> per-lane queues (at most one entry per node of the
+        // batch and lane: the head of the loop leaves room for 32)
         {
             unsigned bl = b_oleaf;
             while (bl) {
@@ -1060,13 +1084,42 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 const int c0 = __shfl_sync(SPHB_FULL_MASK, count, src);
                 const unsigned m = __shfl_sync(SPHB_FULL_MASK, mask, src);
                 const double l2 = __shfl_sync(SPHB_FULL_MASK, hl2, src);
-                queue_leaf((m >> lane) & 1u, f0, c0, l2);
+                if ((m >> lane) & 1u) { lq[nlq * 32] = make_double2(pack_ints(f0, c0), fmax(h_i2, l2)); ++nlq; }
             }
         }
         // ---- fetch the next batch now: its loads are in flight during the per-lane tests
         __syncwarp();
-        pop_load();
-        // (e) mixed nodes: the reference's own per-particle test (src/bhtree.cpp:303-308)
+        {
+            const int ne = min(top, 32);
+            int2 ent = make_int2(0, 0);
+            int nc = 0;
+            if (lane < ne) { ent = sm.stack[top - 1 - lane]; nc = (int)((unsigned)ent.x >> 29) + 1; }
+            int incl = nc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(SPHB_FULL_MASK, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int m = __popc(__ballot_sync(SPHB_FULL_MASK, lane < ne && incl <= 32));   // entries taken (a prefix)
+            k = m > 0 ? __shfl_sync(SPHB_FULL_MASK, incl, m - 1) : 0;
+            if (lane < m) {
+                const int c0 = ent.x & 0x1fffffff;
+                for (int ci = 0; ci < nc; ++ci) sm.expand[incl - nc + ci] = make_int2(c0 + ci, ent.y);
+            }
+            __syncwarp();
+            node = -1;
+            mask = 0;
+            if (lane < k) {
+                const int2 e = sm.expand[lane];
+                node = e.x;
+                mask = (unsigned)e.y;
+                const double2 * q = t.ng + (size_t)node * 4;
+                q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2);
+            }
+            top -= m;
+            __syncwarp();
+        }
+        // (f) mixed nodes: the reference's own per-particle test (src/bhtree.cpp:303-308)
         for (int q = 0; q < nmix; ++q) {
             const double4 c4 = sm.mx[q];
             const double me2 = sm.me2[q];
@@ -1074,9 +1127,8 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             const unsigned mm = sm.mmask[q];
             bool open = false, accept = false;
             if ((mm >> lane) & 1u) {
-                double cc[DIM], d[DIM];
-                vec_from4<DIM>(c4, cc);
-                calc_r_ij<DIM>(P, ri, cc, d);
+                double d[DIM];
+                grav_rij<DIM, PERIODIC>(P, ri, c4, d);
                 const double d2 = abs2_exact<DIM>(d);
                 if (me2 > __dmul_rn(P.theta2, d2)) open = true;
                 else accept = true;
@@ -1086,7 +1138,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             if (cls == 3 && mslot == q) racc = a_b;        // the node's own lane keeps its accept mask
             if (o_b) {
                 if (info.y == 0) {
-                    queue_leaf(open, info.z, info.w, sm.mh2[q]);
+                    if (open) { lq[nlq * 32] = make_double2(pack_ints(info.z, info.w), fmax(h_i2, sm.mh2[q])); ++nlq; }
                 } else if (top + 1 > GV_STACK) {
                     if (lane == 0) atomicOr(&d_err[2], (unsigned long long)WALK_ERR_GRAV_STACK);
                 } else {
@@ -1095,27 +1147,30 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 }
             }
         }
-        // accept masks of the batch, node-major -> particle-major: one word per lane for block npb
-        if (b_acc | b_mix) {
-            const unsigned tw = warp_transpose32(racc, lane);
-#pragma unroll
-            for (int b = 0; b < GV_NB; ++b) if (npb == b) pcw[b] = tw;
-            if (++npb == GV_NB) flush_pc();
+        // accept masks of the batch: rows compacted to the chunk slots, then node-major -> particle-major
+        if (b_sel) {
+            __syncwarp();
+            if ((b_sel >> lane) & 1u) sm.mmask[sslot] = racc;
+            __syncwarp();
+            const int nsel = __popc(b_sel);
+            const unsigned row = lane < nsel ? sm.mmask[lane] : 0u;
+            const unsigned long long tw = (unsigned long long)warp_transpose32(row, lane) << npb;
+            pcw0 |= (unsigned)tw;
+            pcw1 |= (unsigned)(tw >> 32);
+            npb += nsel;
         }
         __syncwarp();
     }
-    flush_pc();
-    flush_pp();
 
     if (valid) {
 #pragma unroll
         for (int a = 0; a < DIM; ++a) p.acc[a][i] = acc[a];
         p.phi[i] = phi;
-        tot_pp += n_pp; tot_pc += n_pc; tot_visit += n_visit; tot_pcg += n_pcg; tot_ppg += n_ppg;
+        if (COUNT) { tot_pp += n_pp; tot_pc += n_pc; tot_visit += n_visit; tot_pcg += n_pcg; tot_ppg += n_ppg; }
     }
     __syncwarp();
     }
-    if (cnt) {
+    if (COUNT) {
         const unsigned long long a = warp_sum_u64(tot_pp), b = warp_sum_u64(tot_pc), cc = warp_sum_u64(tot_visit);
         const unsigned long long pg = warp_sum_u64(tot_pcg), qg = warp_sum_u64(tot_ppg);
         if (lane == 0) { atomicAdd(&cnt->grav_pp, a); atomicAdd(&cnt->grav_pc, b); atomicAdd(&cnt->grav_node_visits, cc);

@@ -12,7 +12,7 @@ import numpy as np
 from .samples import particle_dtype
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsphb.so")
+LIB_PATH = os.environ.get("SPHB_LIB") or os.path.join(_HERE, "libsphb.so")    # SPHB_LIB: developer A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 
 F_POS, F_VEL, F_VEL_P, F_ACC = 1 << 0, 1 << 1, 1 << 2, 1 << 3
