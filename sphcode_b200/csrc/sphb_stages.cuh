@@ -752,6 +752,10 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 #ifndef SPHB_GV_GROUPCELLS
 #define SPHB_GV_GROUPCELLS 1
 #endif
+#ifndef SPHB_GC_UNROLL
+#define SPHB_GC_UNROLL 1
+#endif
+constexpr int GC_UNROLL = SPHB_GC_UNROLL;   // pairs of group cells per loop trip
 constexpr int GV_BLOCKS = SPHB_GV_BLOCKS;   // resident blocks per SM of k_gravity
 constexpr int GRAV_LQ = SPHB_GRAV_LQ;       // leaf queue depth per lane (global scratch, [entry][lane])
 constexpr int GRAV_NEAR = 128;    // softened-pair list depth per lane (global scratch, [entry][lane])
@@ -881,29 +885,18 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 q = 1;
                 if (nlq > 1) en = lq[32];
             }
+            // software pipeline: the records of the NEXT two pairs are loaded before the current two are used
+            bool have = j < jend, two = j + 1 < jend;
+            int j1 = two ? j + 1 : j;
+            double4 p0 = make_double4(0.0, 0.0, 0.0, 0.0), p1 = p0;
+            if (have) { p0 = ldg4(&posm[j]); p1 = ldg4(&posm[j1]); }
             do {
                 int nnear = 0;
-                while (j < jend && nnear <= GRAV_NEAR - 2) {
-                    const bool two = j + 1 < jend;
-                    const int j1 = two ? j + 1 : j;
-                    const double4 p0 = ldg4(&posm[j]);
-                    const double4 p1 = ldg4(&posm[j1]);
-                    double d0[DIM], d1[DIM];
-                    grav_rij<DIM, PERIODIC>(P, ri, p0, d0);
-                    grav_rij<DIM, PERIODIC>(P, ri, p1, d1);
-                    const double r20 = dot<DIM>(d0, d0), r21 = dot<DIM>(d1, d1);
-                    // branch-free: a possibly softened pair contributes 0 here and is listed for pass 2
-                    const bool n0 = r20 < thr2, n1x = r21 < thr2, n1 = two && n1x;
-                    const double y0 = fast_rsqrt(n0 ? 1.0 : r20), y1 = fast_rsqrt(n1x ? 1.0 : r21);
-                    const double gm0 = n0 ? 0.0 : P.G * p0.w, gm1 = (!two || n1x) ? 0.0 : P.G * p1.w;
-                    phi -= gm0 * y0;
-                    phi -= gm1 * y1;
-                    const double s0 = gm0 * y0 * (y0 * y0), s1 = gm1 * y1 * (y1 * y1);
-#pragma unroll
-                    for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
-                    if (n0) { nearq[nnear * 32] = j; ++nnear; }
-                    if (n1) { nearq[nnear * 32] = j1; ++nnear; }
-                    if (COUNT) n_pp += two ? 2 : 1;
+                while (have && nnear <= GRAV_NEAR - 2) {
+                    const double4 c0 = p0, c1 = p1;
+                    const int cj = j, cj1 = j1;
+                    const bool ctwo = two;
+                    const double cthr2 = thr2;
                     j += 2;
                     if (j >= jend) {                            // next leaf: its entry is in registers already
                         const bool more = q < nlq;
@@ -913,6 +906,25 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                         ++q;
                         if (q < nlq) en = lq[q * 32];
                     }
+                    have = j < jend; two = j + 1 < jend;
+                    j1 = two ? j + 1 : j;
+                    if (have) { p0 = ldg4(&posm[j]); p1 = ldg4(&posm[j1]); }
+                    double d0[DIM], d1[DIM];
+                    grav_rij<DIM, PERIODIC>(P, ri, c0, d0);
+                    grav_rij<DIM, PERIODIC>(P, ri, c1, d1);
+                    const double r20 = dot<DIM>(d0, d0), r21 = dot<DIM>(d1, d1);
+                    // branch-free: a possibly softened pair contributes 0 here and is listed for pass 2
+                    const bool n0 = r20 < cthr2, n1x = r21 < cthr2, n1 = ctwo && n1x;
+                    const double y0 = fast_rsqrt(n0 ? 1.0 : r20), y1 = fast_rsqrt(n1x ? 1.0 : r21);
+                    const double gm0 = n0 ? 0.0 : P.G * c0.w, gm1 = (!ctwo || n1x) ? 0.0 : P.G * c1.w;
+                    phi -= gm0 * y0;
+                    phi -= gm1 * y1;
+                    const double s0 = gm0 * y0 * (y0 * y0), s1 = gm1 * y1 * (y1 * y1);
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
+                    if (n0) { nearq[nnear * 32] = cj; ++nnear; }
+                    if (n1) { nearq[nnear * 32] = cj1; ++nnear; }
+                    if (COUNT) n_pp += ctwo ? 2 : 1;
                 }
                 for (int kk = 0; kk < nnear; ++kk) {
                     const int jn = nearq[kk * 32];
@@ -932,7 +944,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
 #pragma unroll
                     for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
                 }
-            } while (j < jend);                                 // only if the softened-pair list ran full
+            } while (have);                                     // only if the softened-pair list ran full
             nlq = 0;
         }
         // (2) accepted cells of the chunk (monopole, src/bhtree.cpp:326-330): every lane runs over ITS
@@ -974,6 +986,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             if (COUNT) n_pc += ngc;
             if (ngc & 1) { if (lane == 0) sm.gcell[ngc] = make_double4(1e30, 1e30, 1e30, 0.0); ++ngc; }   // pad to even with a massless cell
             __syncwarp();
+#pragma unroll (GC_UNROLL)
             for (int kk = 0; kk < ngc; kk += 2) {
                 const double4 c0 = sm.gcell[kk], c1 = sm.gcell[kk + 1];
                 double d0[DIM], d1[DIM];
