@@ -1,0 +1,56 @@
+"""Generates tests/golden/energy_histories.npz from the UNMODIFIED reference (oracle/_ref, built by
+`make -C oracle ref`; only possible where /root/reference exists): the history of
+Output::output_energy's sums {kinetic, thermal, potential} (src/output.cpp:72-83), dt and time over
+STEPS Solver::integrate steps (src/solver.cpp:417-429) of small shock_tube / khi / evrard runs —
+BASELINE.json's "energy-conservation histories must track the reference's".
+
+    python tests/golden/make_energy_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from sphcode_b200 import sample_params, make_sample  # noqa: E402
+from oracle.refsim import RefSim, build  # noqa: E402
+
+ENERGY_CASES = {
+    "shock_tube": ("shock_tube", dict(N=50)),                                           # as shipped (500 particles)
+    "khi": ("khi", dict(N=32, SPHType="disph", useArtificialConductivity=True)),        # BASELINE configs[1] physics
+    "evrard": ("evrard", dict(N=12)),                                                   # configs[3] physics (DISPH + gravity)
+}
+STEPS = 60
+
+
+def history(sim, steps):
+    """energies after initialize and after each step; dt of each step"""
+    e = [sim.energy()]
+    dts = []
+    for _ in range(steps):
+        dts.append(sim.integrate())
+        e.append(sim.energy())
+    return np.array(e, dtype=np.float64), np.array(dts, dtype=np.float64)
+
+
+def main():
+    build("ref")
+    out = {}
+    for name, (sample, over) in ENERGY_CASES.items():
+        p = sample_params(sample, **over)
+        parts = make_sample(p)
+        ref = RefSim(p, parts, p["DIM"], "tree")
+        ref.initialize()
+        e, dts = history(ref, STEPS)
+        out[name + "_energy"] = e
+        out[name + "_dt"] = dts
+        tot = e.sum(axis=1)
+        print(f"{name}: n={len(parts)} t_end={dts.sum():.4g} E0={tot[0]:.6g} drift={abs(tot[-1] - tot[0]) / abs(tot[0]):.2e}")
+    np.savez_compressed(os.path.join(HERE, "energy_histories.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,7 @@ def _ctx(p, parts):
 def _golden_cases():
     import glob
     import os
-    return sorted(os.path.basename(f)[:-4] for f in glob.glob(U.golden_path("*")))
+    return sorted(n for n in (os.path.basename(f)[:-4] for f in glob.glob(U.golden_path("*"))) if n != "energy_histories")
 
 
 def _golden_params(name):
@@ -238,3 +238,92 @@ def test_two_gpu_slices_match_golden():
                         __import__("os").path.join(U.ROOT, "tests", "dist_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("name", ["shock_tube", "khi", "evrard"])
+def test_energy_history_tracks_reference(name):
+    """BASELINE.json north_star: energy-conservation histories of shock_tube, khi and evrard must track the
+    reference's.  60 Solver::integrate steps (the evrard case runs through maximum compression) against the
+    history recorded from the unmodified reference (tests/golden/make_energy_golden.py): every energy sum
+    of src/output.cpp:72-83 and every dt within 1e-9 of the reference's (scale: the largest |E| of the run)."""
+    import sys
+    sys.path.insert(0, U.GOLDEN_DIR)
+    from make_energy_golden import ENERGY_CASES, STEPS, history
+    from sphcode_b200 import sample_params, make_sample
+    g = np.load(U.golden_path("energy_histories"))
+    sample, over = ENERGY_CASES[name]
+    p = sample_params(sample, **over)
+    c = _ctx(p, make_sample(p))
+    c.initialize()
+    e, dts = history(c, STEPS)
+    ge, gdt = g[name + "_energy"], g[name + "_dt"]
+    scale = np.abs(ge).max()
+    err_e = np.abs(e - ge).max() / scale
+    err_dt = (np.abs(dts - gdt) / gdt).max()
+    drift = abs(e[-1].sum() - e[0].sum()) / abs(e[0].sum())
+    gdrift = abs(ge[-1].sum() - ge[0].sum()) / abs(ge[0].sum())
+    print(f"{name}: energy err {err_e:.2e} dt err {err_dt:.2e} drift {drift:.3e} (reference {gdrift:.3e})")
+    assert err_e <= 1e-9 and err_dt <= 1e-9
+    assert c.nonconverged == 0
+
+
+def test_full_size_properties_evrard_1m():
+    """BASELINE configs[3] at its full size (sample/evrard N=124, 998 592 particles), through properties that
+    need no reference run: (1) the SPH pair forces are antisymmetric, so sum m a_fluid vanishes; (2) for a
+    random subsample the density / neighbour count of the device equal a brute-force sum over ALL particles
+    with the reference's operation order (bit-exact count, 1e-10 density); (3) tree gravity of a subsample
+    against the direct sum of src/gravity_force.cpp:16-42,75-81 has the error level of a theta = 0.5 tree."""
+    from sphcode_b200 import sample_params, make_sample
+    p = sample_params("evrard", N=124)
+    parts = make_sample(p)
+    n = len(parts)
+    assert n == 998592
+    c = _ctx(p, parts)
+    c.init_state(); c.make_tree(); c.pre(); c.fluid()
+    s = c.particles
+    m = s["mass"]
+    # (1)
+    tot = (m[:, None] * s["acc"]).sum(axis=0)
+    mag = (m * U.vnorm(s["acc"])).sum()
+    assert np.abs(tot).max() <= 1e-11 * mag, (tot, mag)
+    # (2)
+    rng = np.random.default_rng(7)
+    idx = rng.choice(n, 192, replace=False)
+    pos = s["pos"]
+    sigma = 495.0 / (32.0 * np.pi)
+    for i in idx:
+        d = pos[i] - pos
+        r2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+        h = s["sml"][i]
+        sel = np.nonzero(r2 < (h * 1.3) ** 2)[0]
+        r = np.sqrt(r2[sel])
+        inside = r < h
+        assert int(inside.sum()) == int(s["neighbor"][i]), (i, int(inside.sum()), int(s["neighbor"][i]))
+        q = r[inside] / h
+        w = sigma / h ** 3 * (1 - q) ** 6 * (1 + 6 * q + 35.0 / 3.0 * q * q)
+        dens = (m[sel][inside] * w).sum()
+        assert abs(dens - s["dens"][i]) <= RTOL * dens, (i, dens, s["dens"][i])
+    # (3)
+    fluid_acc = s["acc"].copy()
+    c.gravity()
+    g = c.particles
+    ga = g["acc"] - fluid_acc
+    def soft_g(r, h):
+        """g of src/gravity_force.cpp:32-44 (Hernquist & Katz 1989), vectorised"""
+        e = 0.5 * h
+        u = r / e
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inner = (4.0 / 3.0 - 1.2 * u * u + 0.5 * u ** 3) / e ** 3
+            mid = (-1.0 / 15 + 8.0 / 3 * u ** 3 - 3 * u ** 4 + 1.2 * u ** 5 - u ** 6 / 6.0) / r ** 3
+            outer = 1.0 / r ** 3
+        return np.where(u < 1.0, inner, np.where(u < 2.0, mid, outer))
+    errs = []
+    for i in idx[:64]:
+        d = pos[i] - pos
+        r = np.sqrt((d * d).sum(axis=1))
+        gg = 0.5 * (soft_g(r, s["sml"][i]) + soft_g(r, s["sml"]))      # src/gravity_force.cpp:75-81
+        a = -(p["G"] * (m * gg)[:, None] * d).sum(axis=0)
+        errs.append(U.vnorm(ga[i] - a) / U.vnorm(a))
+    errs = np.array(errs)
+    print("gravity subsample: median rel err", np.median(errs), "max", errs.max())
+    assert np.median(errs) < 5e-3 and errs.max() < 5e-2

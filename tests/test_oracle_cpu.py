@@ -30,7 +30,7 @@ def _build_port():
     refsim.build("port")
 
 
-GOLD = sorted(os.path.basename(f)[:-4] for f in glob.glob(U.golden_path("*")))
+GOLD = sorted(n for n in (os.path.basename(f)[:-4] for f in glob.glob(U.golden_path("*"))) if n in GOLDEN)
 
 
 def _gp(name):
@@ -127,3 +127,20 @@ def test_kernel_derivatives_known_answer(dim, kernel):
             rij = np.array([r * 0.6, r * 0.0, r * 0.8])
             a, b = sim.kernel_eval(rij, 0.9), ref.kernel_eval(rij, 0.9)
             np.testing.assert_allclose(np.hstack([a[0], a[1], a[2]]), np.hstack([b[0], b[1], b[2]]), rtol=1e-13, atol=1e-300)
+
+
+@pytest.mark.parametrize("name", ["shock_tube", "khi", "evrard"])
+def test_port_energy_history_matches_golden(name):
+    """The port tracks the unmodified reference's energy history over 60 steps (tests/golden/
+    make_energy_golden.py; evrard runs through maximum compression)."""
+    from make_energy_golden import ENERGY_CASES, STEPS, history
+    from sphcode_b200 import make_sample
+    g = np.load(U.golden_path("energy_histories"))
+    sample, over = ENERGY_CASES[name]
+    p = sample_params(sample, **over)
+    sim = RefSim(p, make_sample(p), p["DIM"], "port")
+    sim.initialize()
+    e, dts = history(sim, STEPS)
+    ge, gdt = g[name + "_energy"], g[name + "_dt"]
+    assert np.abs(e - ge).max() <= 1e-9 * np.abs(ge).max()
+    assert (np.abs(dts - gdt) / gdt).max() <= 1e-9
