@@ -269,19 +269,26 @@ k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
         int ncand = 0;
         {
             const int nraw_max = __reduce_max_sync(SPHB_FULL_MASK, nraw);
-            for (int k = 0; k < nraw_max; ++k) {
-                if (k < nraw) {
-                    const int j = lj[k * 32 + lane];
-                    const double4 pj = ldg4(&rc.posm[j]);
-                    double d[DIM];
-                    rij_from4<DIM>(P, ri, pj, d);
-                    const double r2 = abs2_exact<DIM>(d);
-                    if (r2 < hs2) {
-                        lr[ncand * 32 + lane] = sqrt(r2);
-                        lj[ncand * 32 + lane] = j;
-                        if (NEED_M) lm[ncand * 32 + lane] = pj.w;
-                        ++ncand;
-                    }
+            // two raw hits per trip: both gathers are in flight before the first is used
+            for (int k0 = 0; k0 < nraw_max; k0 += 2) {
+                const bool in0 = k0 < nraw, in1 = k0 + 1 < nraw;
+                const int j0 = in0 ? lj[k0 * 32 + lane] : i, j1 = in1 ? lj[(k0 + 1) * 32 + lane] : i;
+                const double4 p0 = ldg4(&rc.posm[valid ? j0 : 0]), p1 = ldg4(&rc.posm[valid ? j1 : 0]);
+                double d0[DIM], d1[DIM];
+                rij_from4<DIM>(P, ri, p0, d0);
+                rij_from4<DIM>(P, ri, p1, d1);
+                const double r20 = abs2_exact<DIM>(d0), r21 = abs2_exact<DIM>(d1);
+                if (in0 && r20 < hs2) {
+                    lr[ncand * 32 + lane] = sqrt(r20);
+                    lj[ncand * 32 + lane] = j0;
+                    if (NEED_M) lm[ncand * 32 + lane] = p0.w;
+                    ++ncand;
+                }
+                if (in1 && r21 < hs2) {
+                    lr[ncand * 32 + lane] = sqrt(r21);
+                    lj[ncand * 32 + lane] = j1;
+                    if (NEED_M) lm[ncand * 32 + lane] = p1.w;
+                    ++ncand;
                 }
             }
         }
@@ -300,6 +307,7 @@ k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
                 kc.init(h);
                 double s = 0.0, sd = 0.0;
                 const int nk = done ? 0 : ncand;
+#pragma unroll 4
                 for (int k = 0; k < ncand_max; ++k) {
                     if (k < nk) {
                         const double r = lr[k * 32 + lane];
@@ -347,23 +355,28 @@ k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
             for (int k = 0; k < DIM; ++k) dv.dv[k][a] = 0.0;
         }
         {
-            // every lane skips ahead to its next candidate with r < h (the `break` of the sorted loop,
-            // src/pre_interaction.cpp:87-91), then all lanes run the pair body together
+            // the reference's sorted loop breaks at the first r >= h (src/pre_interaction.cpp:87-91): here the
+            // entries with r < h are first compacted in place by all lanes together (independent, coalesced
+            // column reads; the write cursor never passes the read cursor), then every lane runs the pair
+            // body over its dense prefix
             const int nk = valid ? ncand : 0;
-            int k = 0;
-            for (;;) {
-                double r = 0.0;
-                while (k < nk) {
-                    r = lr[k * 32 + lane];
-                    if (r < h) break;
-                    ++k;
+            int nn = 0;
+            for (int k0 = 0; k0 < ncand_max; k0 += 4) {
+                double r4[4]; int j4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool in = k0 + u < nk;
+                    r4[u] = in ? lr[(k0 + u) * 32 + lane] : 1.7976931348623157e308;
+                    j4[u] = in ? lj[(k0 + u) * 32 + lane] : 0;
                 }
-                const bool act = k < nk;
-                if (!__any_sync(SPHB_FULL_MASK, act)) break;
-                if (act) {
-                    dv.pair(lj[k * 32 + lane], r);
-                    ++k;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (r4[u] < h) { lr[nn * 32 + lane] = r4[u]; lj[nn * 32 + lane] = j4[u]; ++nn; }
                 }
+            }
+            const int nn_max = __reduce_max_sync(SPHB_FULL_MASK, nn);
+            for (int k = 0; k < nn_max; ++k) {
+                if (k < nn) dv.pair(lj[k * 32 + lane], lr[k * 32 + lane]);
             }
         }
 
