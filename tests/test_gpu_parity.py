@@ -327,3 +327,41 @@ def test_full_size_properties_evrard_1m():
     errs = np.array(errs)
     print("gravity subsample: median rel err", np.median(errs), "max", errs.max())
     assert np.median(errs) < 5e-3 and errs.max() < 5e-2
+
+
+def test_cli_run_matches_library(tmp_path):
+    """sph_gpu <sample> (the reference's command line on the device path, Solver::run src/solver.cpp:301-350):
+    energy.dat and the last snapshot in the reference's text formats (src/output.cpp:14-90) agree with the same
+    run driven through the C ABI from Python."""
+    import os
+    import subprocess
+    from sphcode_b200 import sample_params, make_sample
+    exe = os.path.join(U.ROOT, "sphcode_b200", "host", "sph_gpu")
+    assert os.path.exists(exe), "sphcode_b200/host/sph_gpu is missing: run __graft_entry__.build()"
+    out = str(tmp_path / "res")
+    r = subprocess.run([exe, "evrard", "--set", "N=12", "--set", "endTime=0.05", "--set", "outputTime=0.02",
+                        "--set", f"outputDirectory={out}"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "calclation time" in r.stdout
+    p = sample_params("evrard", N=12, endTime=0.05, outputTime=0.02)
+    c = _ctx(p, make_sample(p))
+    c.initialize()
+    t, t_out, rows, snaps = 0.0, 0.02, [(0.0, *c.energy())], 1
+    while t < 0.05:
+        t += c.integrate()
+        if t > t_out:
+            rows.append((t, *c.energy()))
+            t_out += 0.02
+            snaps += 1
+    en = np.loadtxt(os.path.join(out, "energy.dat"))
+    assert en.shape == (len(rows), 5)
+    ref = np.array([[a, k, th, po, k + th + po] for a, k, th, po in rows])
+    np.testing.assert_allclose(en, ref, rtol=2e-5, atol=1e-12)          # default ostream precision: 6 digits
+    files = sorted(f for f in os.listdir(out) if f.endswith(".dat") and f != "energy.dat")
+    assert files == [f"{k:05d}.dat" for k in range(snaps)]
+    last = np.loadtxt(os.path.join(out, files[-1]))
+    s = c.particles
+    assert last.shape == (len(s), 3 * 3 + 9)
+    np.testing.assert_allclose(last[:, 0:3], s["pos"], rtol=2e-5, atol=1e-12)
+    np.testing.assert_allclose(last[:, 10], s["dens"], rtol=2e-5)
+    assert np.array_equal(last[:, 14].astype(int), s["id"]) and np.array_equal(last[:, 15].astype(int), s["neighbor"])

@@ -151,3 +151,67 @@ def test_multi_rank_host_logic_gloo():
         p_.join(timeout=60)
     assert all(r[1] == bytes(range(128)) for r in res)
     assert all(r[2] for r in res) and all(r[3] == 1.0 for r in res)
+
+
+def _sph_gpu():
+    import os
+    import subprocess
+    exe = os.path.join(U.ROOT, "sphcode_b200", "host", "sph_gpu")
+    if not os.path.exists(exe):
+        r = subprocess.run(["make", "-C", os.path.dirname(exe), "sph_gpu"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+    return exe
+
+
+@pytest.mark.parametrize("name,N", [("shock_tube", 50), ("khi", 32), ("gresho_chan_vortex", 24), ("pairing_instability", 16),
+                                    ("hydrostatic", 16), ("evrard", 14)])
+def test_cli_initial_conditions_match_generators(name, N, tmp_path):
+    """sph_gpu (C++ host: JSON reader, sample registry, generators) builds the same particle
+    set as the Python restatement of src/sample/*.cpp that the golden vectors were made from: bit-exact, except
+    evrard where libm's pow and numpy's differ in the last bit."""
+    import subprocess
+    from sphcode_b200 import sample_params, make_sample
+    from sphcode_b200.samples import particle_dtype
+    out = str(tmp_path / "ic.bin")
+    r = subprocess.run([_sph_gpu(), name, "--set", f"N={N}", "--dump-ic", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p = sample_params(name, N=N)
+    ref = make_sample(p)
+    got = np.fromfile(out, dtype=particle_dtype(p["DIM"]))
+    assert len(got) == len(ref)
+    for f in ref.dtype.names:
+        if f == "next":
+            continue
+        if name == "evrard":
+            np.testing.assert_allclose(got[f], ref[f], rtol=2e-15, atol=0)
+        else:
+            assert np.array_equal(got[f], ref[f]), f
+
+
+def test_cli_parameter_errors(tmp_path):
+    """Error texts and exit status of Solver::read_parameterfile (src/solver.cpp:155-299) / exception_handler."""
+    import json
+    import subprocess
+    exe = _sph_gpu()
+    ic = str(tmp_path / "ic.bin")
+
+    def run(*args):
+        r = subprocess.run([exe, *args, "--dump-ic", ic], capture_output=True, text=True)
+        return r.returncode, r.stderr
+
+    assert run("evrard", "--set", "SPHType=foo") == (1, "error: Unknown SPH type\n")
+    assert run("evrard", "--set", "kernel=gauss") == (1, "error: kernel is unknown.\n")
+    assert run("khi", "--set", "rangeMax=[1.0]") == (1, "error: rangeMax != DIM\n")
+    assert run("khi", "--set", "endTime=-1") == (1, "error: endTime < startTime\n")
+    assert run("khi", "--set", "useTimeDependentAV=true", "--set", "alphaMax=0.01") == (1, "error: alphaMax < alphaMin\n")
+    rc, err = run(str(tmp_path / "missing.json"))
+    assert rc == 1 and "cannot open file" in err
+    # a parameter file of the reference has no sample: "unknown sample type." (src/solver.cpp:491); with the key it runs
+    pf = tmp_path / "p.json"
+    pf.write_text(json.dumps({"outputDirectory": str(tmp_path), "endTime": 0.1, "gamma": 1.4}))
+    assert run(str(pf)) == (1, "error: unknown sample type.\n")
+    pf.write_text(json.dumps({"outputDirectory": str(tmp_path), "endTime": 0.1, "gamma": 1.4, "sample": "shock_tube", "N": 20,
+                              "periodic": True, "rangeMax": [1.5], "rangeMin": [-0.5], "neighborNumber": 4}))
+    assert run(str(pf))[0] == 0
+    pf.write_text(json.dumps({"outputDirectory": str(tmp_path), "endTime": 0.1, "sample": "shock_tube"}))
+    assert run(str(pf)) == (1, "error: No such node (gamma)\n")
