@@ -39,6 +39,8 @@ CONFIGS = {
     "evrard_gsph": ("evrard", dict(N=16, SPHType="gsph")),
     "evrard_noiter": ("evrard", dict(N=16, iterativeSmoothingLength=False)),
     "evrard_leaf1": ("evrard", dict(N=12, leafParticleNumber=1)),
+    "evrard_shallow": ("evrard", dict(N=16, maxTreeLevel=2)),                        # leaves of several hundred particles
+    "khi_shallow": ("khi", dict(N=32, maxTreeLevel=3, SPHType="disph")),
 }
 
 
