@@ -270,9 +270,18 @@ def main():
     achieved = grav_flops / (grav_ms * 1e-3) / 1e12 if grav_ms > 0 else 0.0
     sph_flops = 57.0 * cnt["newton_evals"] + 78.0 * cnt["pre_neighbors"] + 57.0 * cnt["pre_neighbors"] + 141.0 * cnt["force_pairs"]
     step_flops = grav_flops + sph_flops
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this
+    # workload (profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum); 1-GPU figure
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if world == 1 and tj.get("n_side") == args.n_side:
+            traffic = tj["k_gravity"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
-        "bound": "fp64", "kernel": "k_gravity<3>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+        "bound": "fp64", "kernel": "k_gravity<3,false,false>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": achieved / fp64_peak if fp64_peak else None, "traffic": traffic,
         "peak_source": "FP64 FMA micro-benchmark sphb_bench_fp64, measured in this run",
         "alg_flops_per_launch": grav_flops, "ms_per_launch": grav_ms,
         "hbm": {"achieved": grav_bytes / (grav_ms * 1e-3) / 1e9 if grav_ms > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",

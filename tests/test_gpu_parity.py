@@ -365,3 +365,49 @@ def test_cli_run_matches_library(tmp_path):
     np.testing.assert_allclose(last[:, 0:3], s["pos"], rtol=2e-5, atol=1e-12)
     np.testing.assert_allclose(last[:, 10], s["dens"], rtol=2e-5)
     assert np.array_equal(last[:, 14].astype(int), s["id"]) and np.array_equal(last[:, 15].astype(int), s["neighbor"])
+
+
+@pytest.mark.parametrize("sample,over,n_expect", [
+    ("khi", dict(N=1152, SPHType="disph", useArtificialConductivity=True), 995328),          # BASELINE configs[1]
+    ("gresho_chan_vortex", dict(N=2048, SPHType="gsph", use2ndOrderGSPH=True), 4194304),      # BASELINE configs[2]
+])
+def test_full_size_properties_2d(sample, over, n_expect):
+    """BASELINE configs[1] and [2] at their full sizes (periodic 2-D boxes), by properties that need no reference
+    run: antisymmetric pair forces (sum m a = 0), brute-force density / neighbour count of a random subsample
+    over ALL particles with the minimum image, and two clean steps (finite dt, no Newton fallback)."""
+    from sphcode_b200 import sample_params, make_sample
+    p = sample_params(sample, **over)
+    parts = make_sample(p)
+    n = len(parts)
+    assert n == n_expect
+    c = _ctx(p, parts)
+    c.initialize()
+    s = c.particles
+    m = s["mass"]
+    tot = (m[:, None] * s["acc"]).sum(axis=0)
+    mag = (m * U.vnorm(s["acc"])).sum()
+    assert np.abs(tot).max() <= 1e-10 * mag, (tot, mag)
+    rng = np.random.default_rng(11)
+    idx = rng.choice(n, 96, replace=False)
+    pos = s["pos"]
+    L = np.asarray(p["rangeMax"]) - np.asarray(p["rangeMin"])
+    sigma = 9.0 / np.pi                                   # Wendland C4, DIM = 2 (include/kernel/wendland_kernel.hpp:14-20)
+    for i in idx:
+        d = pos[i] - pos
+        d = np.where(d > 0.5 * L, d - L, np.where(d < -0.5 * L, d + L, d))
+        r2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
+        h = s["sml"][i]
+        sel = np.nonzero(r2 < (h * 1.3) ** 2)[0]
+        r = np.sqrt(r2[sel])
+        inside = r < h
+        assert abs(int(inside.sum()) - int(s["neighbor"][i])) <= int(np.sum(np.abs(r - h) <= 1e-12 * h)), i
+        q = r[inside] / h
+        w = sigma / h ** 2 * (1 - q) ** 6 * (1 + 6 * q + 35.0 / 3.0 * q * q)
+        dens = (m[sel][inside] * w).sum()
+        assert abs(dens - s["dens"][i]) <= RTOL * dens, (i, dens, s["dens"][i])
+    e0 = c.energy().sum()
+    for _ in range(2):
+        dt = c.integrate()
+        assert np.isfinite(dt) and dt > 0
+    assert c.nonconverged == 0
+    assert abs(c.energy().sum() - e0) <= 1e-6 * abs(e0)
