@@ -129,6 +129,7 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
             hits &= hits - 1;
             v.hit(sm.tilej[kb]);
         }
+        __syncwarp();                                    // the tile is refilled next: every lane is done reading it
     };
 
     // FP32 image of the m candidates whose indices sit in sm.tilej
