@@ -97,7 +97,8 @@ struct sphb_ctx {
     int * grp_start = nullptr;             // first particle of every group, ascending
     int * d_ngroups = nullptr;             // number of groups (device)
     int * d_grp_ctl = nullptr;             // [0] work counter, [1] end group of the current kernel
-    double2 * grav_lq = nullptr; int * grav_near = nullptr;   // per-warp leaf queues of the gravity walk
+    double2 * grav_lq = nullptr; int * grav_near = nullptr;   // per-warp leaf queues / softened-pair lists of the gravity walk
+    bool grav_attr_set[2][2] = {{false, false}, {false, false}};   // dynamic-smem attribute set for k_gravity<DIM, PER, CNT>
     Recs rc{};                             // packed gather records (tree order)
     bool recs_dirty = true;                // SoA fields changed since the records were packed
 
@@ -569,7 +570,7 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
         if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
         const int smem = (int)(4 * sizeof(GravSmem));
 #define SPHB_GRAV(PER, CNT) do { \
-            static bool attr_set = false; \
+            bool & attr_set = c->grav_attr_set[PER ? 1 : 0][CNT ? 1 : 0];      /* per context: the attribute is per device */ \
             if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity<DIM, PER, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; } \
             k_gravity<DIM, PER, CNT><<<c->grav_grid, 128, smem, c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, \
                 c->grav_lq, c->grav_near, c->d_cnt, c->d_err); } while (0)
