@@ -21,6 +21,7 @@ using namespace sphb;
 
 namespace {
 
+constexpr int SPHB_MAX_LEVELS = 72;      // tree levels (maxTreeLevel * DIM <= 63 -> at most 64)
 std::string g_create_error;
 
 // ---- minimal NCCL binding (dlopen: single-GPU use must not need libnccl) ----------------------
@@ -80,6 +81,7 @@ struct sphb_ctx {
     int node_cap = 0;
     std::vector<std::pair<int, int>> levels;
     int * lvl_tmp = nullptr, * lvl_offs = nullptr;
+    int * d_lvl = nullptr, * d_lvl_bad = nullptr;   // speculative tree build: level bounds / failure flag on the device
     bool tree_valid = false;
 
     double * d_root = nullptr;             // centre[3], edge
@@ -389,12 +391,55 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     const int max_level_eff = std::min(c->P.max_level, c->P.key_levels);
     const long long node_limit = 5LL * n + 1;          // BHTree::resize: 5 N nodes + the root (src/bhtree.cpp:46)
     k_root_init<<<1, 32, 0, c->stream>>>(c->tb, n, c->d_root); LAUNCH_CHECK();
-    c->levels.clear();
     int lb = 0, le = 1;
+    bool built = false;
+    // ---- speculative build: the level widths of the previous tree (+25 %) size the grids, the level bounds
+    // stay on the device, and the host synchronises ONCE at the end instead of once per level.  Any surprise
+    // (a level wider than its grid, a deeper tree, a full node pool) falls back to the exact loop below.
+    if (!c->levels.empty() && c->levels.size() + 3 <= SPHB_MAX_LEVELS) {
+        const std::vector<std::pair<int, int>> prev = c->levels;
+        const int nl = (int)prev.size() + 1;                  // one level more than last time, must come out empty
+        auto cap_of = [&](int l) -> int {
+            if (l == 0) return 1;
+            const long long w = l < (int)prev.size() ? prev[l].second - prev[l].first : 0;
+            return (int)std::min<long long>(c->node_cap, w + w / 4 + 1024);
+        };
+        int init[3] = {0, 1, 0};
+        CK(cudaMemcpyAsync(c->d_lvl, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->d_lvl_bad, 0, sizeof(int), c->stream));
+        for (int l = 0; l < nl; ++l) {
+            const int wc = cap_of(l);
+            k_level_count<DIM><<<cdiv((long long)wc << DIM, B), B, 0, c->stream>>>(c->tb, keys, 0, 0, c->P.leaf_num, max_level_eff,
+                c->P.key_levels, c->lvl_tmp, c->d_lvl + l, wc);
+            LAUNCH_CHECK();
+            size_t tb = c->cub_tmp_bytes;
+            CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->lvl_tmp, c->lvl_offs, wc, c->stream));
+            ++c->launches;
+            k_level_advance<<<1, 32, 0, c->stream>>>(c->d_lvl + l, c->lvl_tmp, c->lvl_offs, cap_of(l + 1), c->node_cap, c->d_lvl_bad); LAUNCH_CHECK();
+            k_level_emit<DIM><<<cdiv((long long)wc << DIM, B), B, 0, c->stream>>>(c->tb, keys, 0, 0, c->P.leaf_num, max_level_eff,
+                c->P.key_levels, c->lvl_offs, c->d_root, c->d_lvl + l, c->d_lvl_bad);
+            LAUNCH_CHECK();
+        }
+        int h_lvl[SPHB_MAX_LEVELS + 2], bad = 0;
+        CK(cudaMemcpyAsync(h_lvl, c->d_lvl, (size_t)(nl + 2) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&bad, c->d_lvl_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (!bad && h_lvl[nl + 1] == h_lvl[nl]) {             // the extra level is empty: the tree is complete
+            c->levels.clear();
+            for (int l = 0; l < nl && h_lvl[l + 1] > h_lvl[l]; ++l) c->levels.push_back({h_lvl[l], h_lvl[l + 1]});
+            lb = h_lvl[nl];
+            built = true;
+        } else {
+            k_root_init<<<1, 32, 0, c->stream>>>(c->tb, n, c->d_root); LAUNCH_CHECK();
+        }
+    }
+    if (!built) {
+    c->levels.clear();
+    lb = 0; le = 1;
     while (le > lb) {
         c->levels.push_back({lb, le});
         const int w = le - lb;
-        k_level_count<DIM><<<cdiv(w, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_tmp);
+        k_level_count<DIM><<<cdiv((long long)w << DIM, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_tmp, nullptr, 0);
         LAUNCH_CHECK();
         size_t tb = c->cub_tmp_bytes;
         CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->lvl_tmp, c->lvl_offs, w, c->stream));
@@ -409,9 +454,10 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
             const int ncap = (int)std::min<long long>(node_limit, std::max<long long>(2LL * c->node_cap, (long long)le + total + 1024));
             if (alloc_nodes(c, ncap, le, w)) return 1;
         }
-        k_level_emit<DIM><<<cdiv(w, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_offs, c->d_root);
+        k_level_emit<DIM><<<cdiv((long long)w << DIM, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_offs, c->d_root, nullptr, nullptr);
         LAUNCH_CHECK();
         lb = le; le += total;
+    }
     }
     const int n_nodes = lb;
     for (int l = (int)c->levels.size() - 1; l >= 0; --l) {
@@ -720,6 +766,8 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
     cudaMalloc(&q, 4 * sizeof(unsigned long long)); c->d_err = (unsigned long long *)q;
     cudaMalloc(&q, sizeof(Counters)); c->d_cnt = (Counters *)q;
     cudaMalloc(&q, sizeof(int)); c->d_group_counter = (int *)q;
+    cudaMalloc(&q, (SPHB_MAX_LEVELS + 4) * sizeof(int)); c->d_lvl = (int *)q;
+    cudaMalloc(&q, sizeof(int)); c->d_lvl_bad = (int *)q;
     cudaMalloc(&q, sizeof(int)); c->d_ngroups = (int *)q;
     cudaMalloc(&q, 2 * sizeof(int)); c->d_grp_ctl = (int *)q;
     cudaMemset(c->d_scal, 0, 8 * sizeof(double));
@@ -750,7 +798,7 @@ void sphb_destroy(sphb_ctx * c)
     cudaStreamSynchronize(c->stream);
     if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     free_bag(c->allocs); free_bag(c->node_allocs);
-    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter); cudaFree(c->d_ngroups); cudaFree(c->d_grp_ctl);
+    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter); cudaFree(c->d_lvl); cudaFree(c->d_lvl_bad); cudaFree(c->d_ngroups); cudaFree(c->d_grp_ctl);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->own_stream);

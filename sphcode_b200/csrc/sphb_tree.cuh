@@ -176,62 +176,95 @@ __device__ __forceinline__ bool node_splits(const TreeBuild & t, int i, int leaf
     return t.count[i] > leaf_num && t.level[i] <= max_level_eff;
 }
 
+// One lane per CHILD (2^DIM lanes per node): lane c finds the upper boundary of child c by its own
+// binary search over the node's key range, so the 2^DIM searches of a node run concurrently — the top
+// levels have a handful of nodes with millions of keys each and were pure dependent-load latency with
+// one thread per node.
+template <int DIM>
+__device__ __forceinline__ void child_range(const TreeBuild & t, const unsigned long long * __restrict__ keys, int node, bool splits,
+                                            int key_levels, int c, int & b, int & e)
+{
+    constexpr int NCHILD = 1 << DIM;
+    b = 0; e = 0;
+    if (splits) {
+        const int first = t.first[node], last = first + t.count[node];
+        const int shift = (key_levels - t.level[node]) * DIM;
+        e = (c == NCHILD - 1) ? last : lower_bound_child(keys, first, last, shift, NCHILD - 1, c + 1);
+        b = first;
+    }
+    const int prev = __shfl_up_sync(SPHB_FULL_MASK, e, 1);
+    if (splits && c > 0) b = prev;
+}
+
 template <int DIM>
 __global__ void k_level_count(TreeBuild t, const unsigned long long * __restrict__ keys, int lvl_begin, int lvl_end,
-                              int leaf_num, int max_level_eff, int key_levels, int * __restrict__ tmp)
+                              int leaf_num, int max_level_eff, int key_levels, int * __restrict__ tmp,
+                              const int * __restrict__ lvl /* speculative build: {begin, end} on the device */, int w_cap)
 {
-    const int i = lvl_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= lvl_end) return;
-    int nchild = 0;
-    if (node_splits<DIM>(t, i, leaf_num, max_level_eff)) {
-        constexpr int NCHILD = 1 << DIM;
-        const int first = t.first[i], last = first + t.count[i];
-        const int shift = (key_levels - t.level[i]) * DIM;
-        int b = first;
-        for (int c = 0; c < NCHILD; ++c) {
-            const int e = (c == NCHILD - 1) ? last : lower_bound_child(keys, b, last, shift, NCHILD - 1, c + 1);
-            if (e > b) ++nchild;
-            b = e;
-        }
-    }
-    tmp[i - lvl_begin] = nchild;
+    constexpr int NCHILD = 1 << DIM;
+    if (lvl) { lvl_begin = lvl[0]; lvl_end = lvl[1]; }
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = lvl_begin + tid / NCHILD, c = tid % NCHILD;
+    const bool in = i < lvl_end;
+    const bool splits = in && node_splits<DIM>(t, i, leaf_num, max_level_eff);
+    int b, e;
+    child_range<DIM>(t, keys, i, splits, key_levels, c, b, e);
+    const unsigned full = __ballot_sync(SPHB_FULL_MASK, e > b);
+    const int lane = threadIdx.x & 31;
+    const unsigned grp = (full >> (lane - c)) & ((1u << NCHILD) - 1u);
+    if (in && c == 0) tmp[i - lvl_begin] = __popc(grp);
+    else if (lvl && c == 0 && tid / NCHILD < w_cap) tmp[tid / NCHILD] = 0;       // the scan runs over w_cap entries
 }
 
 template <int DIM>
 __global__ void k_level_emit(TreeBuild t, const unsigned long long * __restrict__ keys, int lvl_begin, int lvl_end,
                              int leaf_num, int max_level_eff, int key_levels, const int * __restrict__ offs,
-                             const double * __restrict__ root)
+                             const double * __restrict__ root,
+                             const int * __restrict__ lvl /* speculative build: {begin, end, next end} */, const int * __restrict__ bad)
 {
-    const int i = lvl_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= lvl_end) return;
-    if (!node_splits<DIM>(t, i, leaf_num, max_level_eff)) {
-        t.child0[i] = -1;
-        t.nchild[i] = 0;
+    constexpr int NCHILD = 1 << DIM;
+    if (lvl) { lvl_begin = lvl[0]; lvl_end = lvl[1]; if (*bad) return; }
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = lvl_begin + tid / NCHILD, c = tid % NCHILD;
+    const bool in = i < lvl_end;
+    const bool splits = in && node_splits<DIM>(t, i, leaf_num, max_level_eff);
+    int b, e;
+    child_range<DIM>(t, keys, i, splits, key_levels, c, b, e);
+    const unsigned full = __ballot_sync(SPHB_FULL_MASK, e > b);
+    const int lane = threadIdx.x & 31;
+    const unsigned grp = (full >> (lane - c)) & ((1u << NCHILD) - 1u);
+    if (!in) return;
+    if (!splits) {
+        if (c == 0) { t.child0[i] = -1; t.nchild[i] = 0; }
         return;
     }
-    constexpr int NCHILD = 1 << DIM;
-    const int first = t.first[i], last = first + t.count[i], level = t.level[i];
-    const int shift = (key_levels - level) * DIM;
+    const int level = t.level[i];
     const int child0 = lvl_end + offs[i - lvl_begin];
-    const double q = ldexp(root[3], -(level - 1)) * 0.25;     // edge of this node / 4 (exact)
-    int b = first, k = 0;
-    for (int c = 0; c < NCHILD; ++c) {
-        const int e = (c == NCHILD - 1) ? last : lower_bound_child(keys, b, last, shift, NCHILD - 1, c + 1);
-        if (e > b) {
-            const int j = child0 + k;
-            t.first[j] = b;
-            t.count[j] = e - b;
-            t.level[j] = level + 1;
-            t.parent[j] = i;
+    if (e > b) {
+        const double q = ldexp(root[3], -(level - 1)) * 0.25;     // edge of this node / 4 (exact)
+        const int j = child0 + __popc(grp & ((1u << c) - 1u));
+        t.first[j] = b;
+        t.count[j] = e - b;
+        t.level[j] = level + 1;
+        t.parent[j] = i;
 #pragma unroll
-            for (int d = 0; d < DIM; ++d)
-                t.center[d][j] = __dadd_rn(t.center[d][i], ((c >> d) & 1) ? q : -q);   // src/bhtree.cpp:190-196
-            ++k;
-        }
-        b = e;
+        for (int d = 0; d < DIM; ++d)
+            t.center[d][j] = __dadd_rn(t.center[d][i], ((c >> d) & 1) ? q : -q);   // src/bhtree.cpp:190-196
     }
-    t.child0[i] = child0;
-    t.nchild[i] = k;
+    if (c == 0) { t.child0[i] = child0; t.nchild[i] = __popc(grp); }
+}
+
+// speculative build: close level l on the device.  lvl = &bounds[l]: {begin, end} -> writes the end of the next
+// level; flags the build as bad if the next level does not fit the grid the host sized for it (w_next_cap)
+// or the node pool.
+__global__ void k_level_advance(int * __restrict__ lvl, const int * __restrict__ tmp, const int * __restrict__ offs,
+                                int w_next_cap, int node_cap, int * __restrict__ bad)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int w = lvl[1] - lvl[0];
+    const int total = (w > 0 && !*bad) ? offs[w - 1] + tmp[w - 1] : 0;
+    if (total > w_next_cap || lvl[1] + total > node_cap) { *bad = 1; lvl[2] = lvl[1]; }
+    else lvl[2] = lvl[1] + total;
 }
 
 __global__ void k_root_init(TreeBuild t, int n, const double * __restrict__ root)
