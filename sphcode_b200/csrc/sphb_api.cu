@@ -81,6 +81,7 @@ struct sphb_ctx {
     int node_cap = 0;
     std::vector<std::pair<int, int>> levels;
     int * lvl_tmp = nullptr, * lvl_offs = nullptr;
+    bool force_full_sort = false;          // redo of a tree build whose partial key sort was too shallow
     int * d_lvl = nullptr, * d_lvl_bad = nullptr;   // speculative tree build: level bounds / failure flag on the device
     bool tree_valid = false;
 
@@ -376,9 +377,18 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         k_bbox_final<DIM><<<1, 32, 0, c->stream>>>(c->d_bbox_part, c->bbox_blocks, c->d_root); LAUNCH_CHECK();
     }
     k_keys<DIM><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, n, c->d_root, c->P.key_levels, c->keys, c->idx); LAUNCH_CHECK();
+    // Partial radix sort: only the key levels the tree can use are sorted — one more than the depth of the
+    // previous tree (the sort is stable and its input is the previous tree order).  If a node below the sorted
+    // levels turns out to need a split, the build is redone with all levels (deeper flag).
+    const int true_max_level = std::min(c->P.max_level, c->P.key_levels);
+    int sort_levels = c->P.key_levels;
+    {
+        const int depth = (int)c->levels.size();
+        if (!c->force_full_sort && depth > 0 && depth <= true_max_level) sort_levels = std::min(c->P.key_levels, depth + 1);
+    }
     size_t tmp = c->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_alt, c->idx, c->idx_alt, n, 0,
-                                       std::min(64, c->P.key_levels * DIM), c->stream));
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_alt, c->idx, c->idx_alt, n,
+                                       (c->P.key_levels - sort_levels) * DIM, std::min(64, c->P.key_levels * DIM), c->stream));
     ++c->launches;
     k_permute<<<cdiv(n, B), B, 0, c->stream>>>(c->d_ptr_cur, c->d_ptr_alt, c->n_darr, c->d_iptr_cur, c->d_iptr_alt, c->n_iarr, c->idx_alt, n);
     LAUNCH_CHECK();
@@ -388,8 +398,9 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     const unsigned long long * keys = c->keys_alt;
 
     if (c->node_cap == 0) { if (alloc_nodes(c, std::max(1024, n / 2 + 64), 0)) return 1; }
-    const int max_level_eff = std::min(c->P.max_level, c->P.key_levels);
+    const int max_level_eff = std::min(true_max_level, sort_levels);
     const long long node_limit = 5LL * n + 1;          // BHTree::resize: 5 N nodes + the root (src/bhtree.cpp:46)
+    CK(cudaMemsetAsync(c->d_lvl_bad, 0, 2 * sizeof(int), c->stream));     // [0] speculation failed, [1] deeper sort needed
     k_root_init<<<1, 32, 0, c->stream>>>(c->tb, n, c->d_root); LAUNCH_CHECK();
     int lb = 0, le = 1;
     bool built = false;
@@ -406,11 +417,10 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         };
         int init[3] = {0, 1, 0};
         CK(cudaMemcpyAsync(c->d_lvl, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemsetAsync(c->d_lvl_bad, 0, sizeof(int), c->stream));
         for (int l = 0; l < nl; ++l) {
             const int wc = cap_of(l);
             k_level_count<DIM><<<cdiv((long long)wc << DIM, B), B, 0, c->stream>>>(c->tb, keys, 0, 0, c->P.leaf_num, max_level_eff,
-                c->P.key_levels, c->lvl_tmp, c->d_lvl + l, wc);
+                c->P.key_levels, c->lvl_tmp, c->d_lvl + l, wc, true_max_level, c->d_lvl_bad + 1);
             LAUNCH_CHECK();
             size_t tb = c->cub_tmp_bytes;
             CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->lvl_tmp, c->lvl_offs, wc, c->stream));
@@ -420,11 +430,12 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
                 c->P.key_levels, c->lvl_offs, c->d_root, c->d_lvl + l, c->d_lvl_bad);
             LAUNCH_CHECK();
         }
-        int h_lvl[SPHB_MAX_LEVELS + 2], bad = 0;
+        int h_lvl[SPHB_MAX_LEVELS + 2], bad[2] = {0, 0};
         CK(cudaMemcpyAsync(h_lvl, c->d_lvl, (size_t)(nl + 2) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(&bad, c->d_lvl_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(bad, c->d_lvl_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        if (!bad && h_lvl[nl + 1] == h_lvl[nl]) {             // the extra level is empty: the tree is complete
+        if (bad[1]) { c->force_full_sort = true; const int r = make_tree_t<DIM>(c); c->force_full_sort = false; return r; }
+        if (!bad[0] && h_lvl[nl + 1] == h_lvl[nl]) {             // the extra level is empty: the tree is complete
             c->levels.clear();
             for (int l = 0; l < nl && h_lvl[l + 1] > h_lvl[l]; ++l) c->levels.push_back({h_lvl[l], h_lvl[l + 1]});
             lb = h_lvl[nl];
@@ -439,7 +450,7 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     while (le > lb) {
         c->levels.push_back({lb, le});
         const int w = le - lb;
-        k_level_count<DIM><<<cdiv((long long)w << DIM, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_tmp, nullptr, 0);
+        k_level_count<DIM><<<cdiv((long long)w << DIM, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_tmp, nullptr, 0, true_max_level, c->d_lvl_bad + 1);
         LAUNCH_CHECK();
         size_t tb = c->cub_tmp_bytes;
         CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp, tb, c->lvl_tmp, c->lvl_offs, w, c->stream));
@@ -457,6 +468,12 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         k_level_emit<DIM><<<cdiv((long long)w << DIM, B), B, 0, c->stream>>>(c->tb, keys, lb, le, c->P.leaf_num, max_level_eff, c->P.key_levels, c->lvl_offs, c->d_root, nullptr, nullptr);
         LAUNCH_CHECK();
         lb = le; le += total;
+    }
+    if (sort_levels < c->P.key_levels) {
+        int deeper = 0;
+        CK(cudaMemcpyAsync(&deeper, c->d_lvl_bad + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (deeper) { c->force_full_sort = true; const int r = make_tree_t<DIM>(c); c->force_full_sort = false; return r; }
     }
     }
     const int n_nodes = lb;
@@ -767,7 +784,7 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
     cudaMalloc(&q, sizeof(Counters)); c->d_cnt = (Counters *)q;
     cudaMalloc(&q, sizeof(int)); c->d_group_counter = (int *)q;
     cudaMalloc(&q, (SPHB_MAX_LEVELS + 4) * sizeof(int)); c->d_lvl = (int *)q;
-    cudaMalloc(&q, sizeof(int)); c->d_lvl_bad = (int *)q;
+    cudaMalloc(&q, 2 * sizeof(int)); c->d_lvl_bad = (int *)q;
     cudaMalloc(&q, sizeof(int)); c->d_ngroups = (int *)q;
     cudaMalloc(&q, 2 * sizeof(int)); c->d_grp_ctl = (int *)q;
     cudaMemset(c->d_scal, 0, 8 * sizeof(double));

@@ -199,7 +199,8 @@ __device__ __forceinline__ void child_range(const TreeBuild & t, const unsigned 
 template <int DIM>
 __global__ void k_level_count(TreeBuild t, const unsigned long long * __restrict__ keys, int lvl_begin, int lvl_end,
                               int leaf_num, int max_level_eff, int key_levels, int * __restrict__ tmp,
-                              const int * __restrict__ lvl /* speculative build: {begin, end} on the device */, int w_cap)
+                              const int * __restrict__ lvl /* speculative build: {begin, end} on the device */, int w_cap,
+                              int true_max_level, int * __restrict__ deeper)
 {
     constexpr int NCHILD = 1 << DIM;
     if (lvl) { lvl_begin = lvl[0]; lvl_end = lvl[1]; }
@@ -207,6 +208,9 @@ __global__ void k_level_count(TreeBuild t, const unsigned long long * __restrict
     const int i = lvl_begin + tid / NCHILD, c = tid % NCHILD;
     const bool in = i < lvl_end;
     const bool splits = in && node_splits<DIM>(t, i, leaf_num, max_level_eff);
+    // the keys are only sorted down to level max_level_eff (partial radix sort): a node below that which the
+    // reference would still split means the sort has to be redone with more levels
+    if (in && c == 0 && i != 0 && !splits && t.count[i] > leaf_num && t.level[i] <= true_max_level) *deeper = 1;
     int b, e;
     child_range<DIM>(t, keys, i, splits, key_levels, c, b, e);
     const unsigned full = __ballot_sync(SPHB_FULL_MASK, e > b);
