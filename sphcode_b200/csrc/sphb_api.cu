@@ -390,8 +390,9 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_alt, c->idx, c->idx_alt, n,
                                        (c->P.key_levels - sort_levels) * DIM, std::min(64, c->P.key_levels * DIM), c->stream));
     ++c->launches;
-    k_permute<<<cdiv(n, B), B, 0, c->stream>>>(c->d_ptr_cur, c->d_ptr_alt, c->n_darr, c->d_iptr_cur, c->d_iptr_alt, c->n_iarr, c->idx_alt, n);
+    k_permute_pack<DIM><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->alt, c->rc, c->idx_alt, n, c->P.sph_type == T_GSPH ? 1 : 0);
     LAUNCH_CHECK();
+    c->recs_dirty = false;
     std::swap(c->cur, c->alt);
     std::swap(c->d_ptr_cur, c->d_ptr_alt);
     std::swap(c->d_iptr_cur, c->d_iptr_alt);
@@ -483,7 +484,6 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     }
     c->td.n_nodes = n_nodes;
     k_tree_scatter<DIM><<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, c->td, n_nodes, c->d_root); LAUNCH_CHECK();
-    if (pack_recs(c, 7)) return 1;
     // particle groups (sphb_tree.cuh): flags at group starts -> ascending list of starts
     CK(cudaMemsetAsync(c->grp_flags, 0, (size_t)n, c->stream));
     k_group_flags<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->world > 1 ? c->slice_groups * 32 : 0, n); LAUNCH_CHECK();

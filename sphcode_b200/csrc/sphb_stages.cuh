@@ -67,6 +67,42 @@ __global__ void k_pack_recs(PSoA p, Recs r, int n, int what)
     }
 }
 
+// Gather-permute of the whole particle state by the sorted index, fused with the packing of the gather
+// records (the values are in registers anyway): replaces k_permute + k_pack_recs(7) in the tree build.
+template <int DIM>
+__global__ void k_permute_pack(PSoA s, PSoA d, Recs r, const int * __restrict__ perm, int n, int gsph)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int q = perm[i];
+    double pos[3] = {0.0, 0.0, 0.0}, vel[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+        pos[a] = s.pos[a][q]; d.pos[a][i] = pos[a];
+        vel[a] = s.vel[a][q]; d.vel[a][i] = vel[a];
+        d.vel_p[a][i] = s.vel_p[a][q];
+        d.acc[a][i] = s.acc[a][q];
+    }
+    const double mass = s.mass[q], dens = s.dens[q], pres = s.pres[q], ene = s.ene[q], sml = s.sml[q], sound = s.sound[q],
+                 balsara = s.balsara[q], alpha = s.alpha[q], gradh = s.gradh[q];
+    d.mass[i] = mass; d.dens[i] = dens; d.pres[i] = pres; d.ene[i] = ene; d.sml[i] = sml; d.sound[i] = sound;
+    d.balsara[i] = balsara; d.alpha[i] = alpha; d.gradh[i] = gradh;
+    d.ene_p[i] = s.ene_p[q]; d.dene[i] = s.dene[q]; d.phi[i] = s.phi[q];
+    d.pid[i] = s.pid[q]; d.neighbor[i] = s.neighbor[q]; d.orig[i] = s.orig[q];
+    if (gsph) {
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) {
+            d.grad_d[a][i] = s.grad_d[a][q]; d.grad_p[a][i] = s.grad_p[a][q];
+#pragma unroll
+            for (int v = 0; v < DIM; ++v) d.grad_v[v][a][i] = s.grad_v[v][a][q];
+        }
+    }
+    r.posm[i] = make_double4(pos[0], pos[1], pos[2], mass);
+    r.velc[i] = make_double4(vel[0], vel[1], vel[2], sound);
+    r.thermo[i] = make_double4(ene, sml, dens, pres);
+    r.av[i] = make_double4(gradh, alpha, balsara, 0.0);
+}
+
 template <int DIM> __device__ __forceinline__ void vec_from4(const double4 & q, double (&o)[DIM])
 {
     o[0] = q.x;

@@ -141,18 +141,6 @@ __global__ void k_keys(PSoA p, int n, const double * __restrict__ root, int key_
     idx[i]  = i;
 }
 
-// Gather-permute of the particle arrays by the sorted index.
-__global__ void k_permute(const double * const * __restrict__ src, double * const * __restrict__ dst, int narr,
-                          const int * const * __restrict__ isrc, int * const * __restrict__ idst, int niarr,
-                          const int * __restrict__ perm, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int s = perm[i];
-    for (int a = 0; a < narr; ++a) dst[a][i] = src[a][s];
-    for (int a = 0; a < niarr; ++a) idst[a][i] = isrc[a][s];
-}
-
 // ---- level-by-level node emission ---------------------------------------------------------------
 __device__ __forceinline__ int lower_bound_child(const unsigned long long * __restrict__ keys, int lo, int hi,
                                                  int shift, unsigned int mask, unsigned int c)
