@@ -217,7 +217,7 @@ int alloc_particles(sphb_ctx * c, int n)
     if (dev_alloc(c, &c->d_bbox_part, (size_t)c->bbox_blocks * 6, c->allocs)) return 1;
 
     // list scratch: one r, j (and m) column set per resident warp of the persistent pre / force kernels
-    c->pre_grid = std::min(cdiv(groups, 4), c->sm_count * 5);       // pre / force: 5 resident blocks per SM
+    c->pre_grid = std::min(cdiv(groups, 4), c->sm_count * PF_BLOCKS);
     c->grav_grid = std::min(cdiv(groups, 4), c->sm_count * GV_BLOCKS);
     const size_t slots = (size_t)c->pre_grid * 4;
     if (dev_alloc(c, &c->scratch_r, slots * c->P.list_cap * 32, c->allocs)) return 1;

@@ -16,6 +16,11 @@
 
 namespace sphb {
 
+#ifndef SPHB_PF_BLOCKS
+#define SPHB_PF_BLOCKS 5
+#endif
+constexpr int PF_BLOCKS = SPHB_PF_BLOCKS;   // resident blocks per SM of k_pre_interaction / k_fluid_force
+
 struct Counters {   // device mirror of sphb_counters (include/sphb.h), all summed over particles
     unsigned long long newton_evals, newton_iters, pre_candidates, pre_neighbors, force_pairs,
                        grav_pp, grav_pc, grav_node_visits, nonconverged, list_overflow,
@@ -254,7 +259,7 @@ struct DensityAcc {
 };
 
 template <int DIM, int KT, int SPH>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, PF_BLOCKS)
 k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
                   double * __restrict__ scratch_r, double * __restrict__ scratch_m, int * __restrict__ scratch_j,
                   const double * __restrict__ d_dt, double * __restrict__ d_hpvs,
@@ -687,7 +692,7 @@ struct ForceAcc {
 };
 
 template <int DIM, int KT, int SPH>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, PF_BLOCKS)
 k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
               int * __restrict__ scratch_j, const double * __restrict__ d_dt,
               unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt)
