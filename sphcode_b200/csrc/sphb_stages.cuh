@@ -308,6 +308,13 @@ k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
         // ... reduced to the candidate set {j : r2 < h_search^2} (src/bhtree.cpp:251-261) by the exact test,
         // all lanes together; columns r, j (and m) are compacted in place
         int ncand = 0;
+        // the sums of the FIRST Newton iteration (h = h0) are taken here, while r is in a register: most
+        // particles converge in one iteration, which then never re-reads the r column
+        const double h0 = hs / P.kernel_ratio;
+        double s_first = 0.0, sd_first = 0.0;
+        unsigned int evals_first = 0;
+        KernelCoef<DIM, KT> kc0;
+        kc0.init(h0);
         {
             const int nraw_max = __reduce_max_sync(SPHB_FULL_MASK, nraw);
             // two raw hits per trip: both gathers are in flight before the first is used
@@ -320,16 +327,28 @@ k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
                 rij_from4<DIM>(P, ri, p1, d1);
                 const double r20 = abs2_exact<DIM>(d0), r21 = abs2_exact<DIM>(d1);
                 if (in0 && r20 < hs2) {
-                    lr[ncand * 32 + lane] = sqrt(r20);
+                    const double r = sqrt(r20);
+                    lr[ncand * 32 + lane] = r;
                     lj[ncand * 32 + lane] = j0;
                     if (NEED_M) lm[ncand * 32 + lane] = p0.w;
                     ++ncand;
+                    if (P.iterative && r < h0) {
+                        s_first += NEED_M ? p0.w * kc0.w(r) : kc0.w(r);
+                        sd_first += NEED_M ? p0.w * kc0.dhw(r) : kc0.dhw(r);
+                        ++evals_first;
+                    }
                 }
                 if (in1 && r21 < hs2) {
-                    lr[ncand * 32 + lane] = sqrt(r21);
+                    const double r = sqrt(r21);
+                    lr[ncand * 32 + lane] = r;
                     lj[ncand * 32 + lane] = j1;
                     if (NEED_M) lm[ncand * 32 + lane] = p1.w;
                     ++ncand;
+                    if (P.iterative && r < h0) {
+                        s_first += NEED_M ? p1.w * kc0.w(r) : kc0.w(r);
+                        sd_first += NEED_M ? p1.w * kc0.dhw(r) : kc0.dhw(r);
+                        ++evals_first;
+                    }
                 }
             }
         }
@@ -338,30 +357,34 @@ k_pre_interaction(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 
         if (P.iterative) {
             // ---- Newton-Raphson (src/pre_interaction.cpp:227-283)
-            const double h0 = hs / P.kernel_ratio;
             const double b = NEED_M ? mass_i * P.ngb / unit_ball<DIM>() : P.ngb / unit_ball<DIM>();
             h = h0;
             bool done = !valid, conv = false;
             for (int it = 0; it < 10; ++it) {
                 if (!__any_sync(SPHB_FULL_MASK, !done)) break;
-                KernelCoef<DIM, KT> kc;
-                kc.init(h);
-                double s = 0.0, sd = 0.0;
-                const int nk = done ? 0 : ncand;
+                double s = s_first, sd = sd_first;
+                if (it == 0) {
+                    if (!done) c_evals += evals_first;
+                } else {
+                    KernelCoef<DIM, KT> kc;
+                    kc.init(h);
+                    s = 0.0; sd = 0.0;
+                    const int nk = done ? 0 : ncand;
 #pragma unroll 4
-                for (int k = 0; k < ncand_max; ++k) {
-                    if (k < nk) {
-                        const double r = lr[k * 32 + lane];
-                        if (r < h) {
-                            if (NEED_M) {
-                                const double m = lm[k * 32 + lane];
-                                s += m * kc.w(r);
-                                sd += m * kc.dhw(r);
-                            } else {
-                                s += kc.w(r);
-                                sd += kc.dhw(r);
+                    for (int k = 0; k < ncand_max; ++k) {
+                        if (k < nk) {
+                            const double r = lr[k * 32 + lane];
+                            if (r < h) {
+                                if (NEED_M) {
+                                    const double m = lm[k * 32 + lane];
+                                    s += m * kc.w(r);
+                                    sd += m * kc.dhw(r);
+                                } else {
+                                    s += kc.w(r);
+                                    sd += kc.dhw(r);
+                                }
+                                ++c_evals;
                             }
-                            ++c_evals;
                         }
                     }
                 }
