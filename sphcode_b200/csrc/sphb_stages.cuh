@@ -854,6 +854,7 @@ struct GravSmem {
     int4     minfo[32];                 //   {child0, nchild, first, count}
     double   mh2[32];                   //   leaves: largest h^2 among the leaf's particles (k_grav_leaf_h)
     unsigned mmask[32];                 //   lane mask; afterwards the accept rows of the batch, compacted
+    int      msl[32];                   //   chunk slot (within the batch) of the mixed node
 };
 
 // Softening functions with the divisions by constants turned into products (soft_fg in
@@ -1141,7 +1142,10 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         // (b) mixed nodes -> list in shared memory (tested lane by lane below)
         const int nmix = __popc(b_mix);
         const int mslot = __popc(b_mix & lt_mask);         // class 3: position in the mixed list
+        const unsigned b_sel = b_acc | b_mix;              // nodes that get a slot of the masked chunk
+        const int sslot = __popc(b_sel & lt_mask);         // position among the batch's chunk cells
         if (cls == 3) {
+            sm.msl[mslot] = sslot;
             sm.mx[mslot] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, mass);
             sm.me2[mslot] = e2;
             sm.minfo[mslot] = make_int4(child0, nchild, first, count);
@@ -1153,9 +1157,7 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         ngc += __popc(b_grp);
         // (d) cells some lanes accept (class 1 with a partial mask: every lane of the mask; class 3: decided
         // below) get the next free chunk slots; racc = lanes that accept this lane's node
-        const unsigned b_sel = b_acc | b_mix;
-        const int sslot = __popc(b_sel & lt_mask);         // position among the batch's chunk cells
-        unsigned racc = (cls == 1 && !grp) ? mask : 0u;
+        const unsigned racc = (cls == 1 && !grp) ? mask : 0u;
         if ((cls == 1 && !grp) || cls == 3) {
             const int e = npb + sslot;
             sm.pcx[e] = c[0];
@@ -1209,38 +1211,58 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             top -= m;
             __syncwarp();
         }
-        // (f) mixed nodes: the reference's own per-particle test (src/bhtree.cpp:303-308)
+        // (f) mixed nodes: the reference's own per-particle test (src/bhtree.cpp:303-308).  Phase 1 is
+        // straight-line (no votes, no branches: the loads and distance chains of successive nodes overlap)
+        // and leaves each lane with its open / accept bits over the mixed list; two bit-matrix transposes
+        // then give lane q the lanes that accept / open mixed node q.
+        unsigned my_open = 0, my_acc = 0;
+#pragma unroll 4
         for (int q = 0; q < nmix; ++q) {
             const double4 c4 = sm.mx[q];
             const double me2 = sm.me2[q];
-            const int4 info = sm.minfo[q];
             const unsigned mm = sm.mmask[q];
-            bool open = false, accept = false;
-            if ((mm >> lane) & 1u) {
-                double d[DIM];
-                grav_rij<DIM, PERIODIC>(P, ri, c4, d);
-                const double d2 = abs2_exact<DIM>(d);
-                if (me2 > __dmul_rn(P.theta2, d2)) open = true;
-                else accept = true;
-            }
-            const unsigned a_b = __ballot_sync(SPHB_FULL_MASK, accept);
-            const unsigned o_b = __ballot_sync(SPHB_FULL_MASK, open);
-            if (cls == 3 && mslot == q) racc = a_b;        // the node's own lane keeps its accept mask
-            if (o_b) {
-                if (info.y == 0) {
-                    if (open) { lq[nlq * 32] = make_double2(pack_ints(info.z, info.w), fmax(h_i2, sm.mh2[q])); ++nlq; }
-                } else if (top + 1 > GV_STACK) {
+            double d[DIM];
+            grav_rij<DIM, PERIODIC>(P, ri, c4, d);
+            const double d2 = abs2_exact<DIM>(d);
+            const bool in = (mm >> lane) & 1u;
+            const bool op = in && me2 > __dmul_rn(P.theta2, d2);
+            my_open |= (op ? 1u : 0u) << q;
+            my_acc |= ((in && !op) ? 1u : 0u) << q;
+        }
+        if (nmix) {
+            const unsigned acc_row = warp_transpose32(my_acc, lane);
+            const unsigned open_row = warp_transpose32(my_open, lane);
+            int4 info = make_int4(0, 0, 0, 0);
+            int msl = 0;
+            if (lane < nmix) { info = sm.minfo[lane]; msl = sm.msl[lane]; }
+            // opened internal nodes: push the children with the mask of the lanes that opened
+            const bool psh = lane < nmix && open_row != 0u && info.y != 0;
+            const unsigned pb = __ballot_sync(SPHB_FULL_MASK, psh);
+            if (pb) {
+                const int total = __popc(pb);
+                if (top + total > GV_STACK) {
                     if (lane == 0) atomicOr(&d_err[2], (unsigned long long)WALK_ERR_GRAV_STACK);
                 } else {
-                    if (lane == 0) sm.stack[top] = make_int2(info.x | ((info.y - 1) << 29), (int)o_b);
-                    top += 1;
+                    if (psh) sm.stack[top + __popc(pb & lt_mask)] = make_int2(info.x | ((info.y - 1) << 29), (int)open_row);
+                    top += total;
                 }
             }
+            // opened leaves: every lane appends the leaves it opened to its queue
+            const unsigned leaf_bits = __ballot_sync(SPHB_FULL_MASK, lane < nmix && info.y == 0);
+            unsigned lb = my_open & leaf_bits;
+            while (lb) {
+                const int q = __ffs(lb) - 1;
+                lb &= lb - 1;
+                const int4 inf = sm.minfo[q];
+                lq[nlq * 32] = make_double2(pack_ints(inf.z, inf.w), fmax(h_i2, sm.mh2[q]));
+                ++nlq;
+            }
+            __syncwarp();                                  // the lane masks in sm.mmask are dead now
+            if (lane < nmix) sm.mmask[msl] = acc_row;      // accept row of mixed node `lane` at its chunk slot
         }
         // accept masks of the batch: rows compacted to the chunk slots, then node-major -> particle-major
         if (b_sel) {
-            __syncwarp();
-            if ((b_sel >> lane) & 1u) sm.mmask[sslot] = racc;
+            if (cls == 1 && !grp) sm.mmask[sslot] = racc;
             __syncwarp();
             const int nsel = __popc(b_sel);
             const unsigned row = lane < nsel ? sm.mmask[lane] : 0u;
