@@ -411,3 +411,38 @@ def test_full_size_properties_2d(sample, over, n_expect):
         assert np.isfinite(dt) and dt > 0
     assert c.nonconverged == 0
     assert abs(c.energy().sum() - e0) <= 1e-6 * abs(e0)
+
+
+def test_tree_rebuild_after_drastic_change_matches_fresh_context():
+    """The tree build speculates on the previous tree (level widths for the grids, depth for the partial key
+    sort) and must fall back to the exact loop / the full sort when the particle distribution changes under it:
+    a context that first built the tree of a sphere and is then handed the same particles squeezed into a
+    dense core plus a far halo (much deeper, differently shaped tree) has to produce the tree, the neighbour
+    sets and the tree gravity of a fresh context."""
+    from sphcode_b200 import sample_params, make_sample
+    p = sample_params("evrard", N=20)
+    parts = make_sample(p)
+    squeezed = parts.copy()
+    r = U.vnorm(parts["pos"])
+    core = r < 0.6
+    squeezed["pos"][core] *= 1e-3                         # dense core: many more tree levels
+    squeezed["pos"][~core] *= 7.0                         # far halo: much larger root cube
+    squeezed["sml"] = np.where(core, 2e-4, 1.5)
+    h = squeezed["sml"].copy()
+    a = _ctx(p, parts)
+    a.initialize()
+    a.integrate()
+    a.upload(squeezed)                                    # same context, new distribution
+    a.make_tree()
+    b = _ctx(p, squeezed)
+    b.make_tree()
+    ka, kb = a.counters(), b.counters()
+    assert ka["tree_nodes"] == kb["tree_nodes"] and ka["tree_leaves"] == kb["tree_leaves"] and ka["n_groups"] == kb["n_groups"]
+    assert kb["tree_nodes"] > 0
+    for sym in (False, True):
+        assert U.lists_equal(a.neighbor_lists(h=h, symmetric=sym), b.neighbor_lists(h=h, symmetric=sym))
+    a.gravity(); b.gravity()
+    pa, pb = a.particles, b.particles
+    assert np.array_equal(pa["id"], pb["id"])
+    np.testing.assert_allclose(pa["phi"], pb["phi"], rtol=1e-12)
+    np.testing.assert_allclose(pa["acc"], pb["acc"], rtol=1e-10, atol=1e-12 * np.abs(pb["acc"]).max())
