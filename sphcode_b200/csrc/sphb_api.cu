@@ -97,8 +97,10 @@ struct sphb_ctx {
 
     double * scratch_r = nullptr, * scratch_m = nullptr; int * scratch_j = nullptr; int pre_grid = 0, grav_grid = 0;
     unsigned char * grp_flags = nullptr;   // 1 where a group starts (tree order)
-    int * grp_start = nullptr;             // first particle of every group, ascending
+    int * grp_start = nullptr;             // first particle of every group, ascending (neighbour walks)
     int * d_ngroups = nullptr;             // number of groups (device)
+    int * grp_start_g = nullptr;           // the same for the gravity walk (larger group cells)
+    int * d_ngroups_g = nullptr;
     int * d_grp_ctl = nullptr;             // [0] work counter, [1] end group of the current kernel
     double2 * grav_lq = nullptr; int * grav_near = nullptr;   // per-warp leaf queues / softened-pair lists of the gravity walk
     bool grav_attr_set[2][2] = {{false, false}, {false, false}};   // dynamic-smem attribute set for k_gravity<DIM, PER, CNT>
@@ -224,7 +226,8 @@ int alloc_particles(sphb_ctx * c, int n)
     if (dev_alloc(c, &c->scratch_j, slots * c->P.list_cap * 32, c->allocs)) return 1;
     if (c->P.sph_type != T_DISPH) { if (dev_alloc(c, &c->scratch_m, slots * c->P.list_cap * 32, c->allocs)) return 1; }
     else c->scratch_m = nullptr;
-    if (dev_alloc(c, &c->grp_flags, np + 32, c->allocs) || dev_alloc(c, &c->grp_start, np + 32, c->allocs)) return 1;
+    if (dev_alloc(c, &c->grp_flags, np + 32, c->allocs) || dev_alloc(c, &c->grp_start, np + 32, c->allocs) ||
+        dev_alloc(c, &c->grp_start_g, np + 32, c->allocs)) return 1;
     if (c->P.use_gravity) {
         if (dev_alloc(c, &c->grav_lq, slots * GRAV_LQ * 32, c->allocs) || dev_alloc(c, &c->grav_near, slots * GRAV_NEAR * 32, c->allocs)) return 1;
     }
@@ -359,10 +362,11 @@ int pack_recs(sphb_ctx * c, int what)
 int ensure_recs(sphb_ctx * c) { return c->recs_dirty ? pack_recs(c, 7) : 0; }
 
 // group table view for a kernel that works on the particles [p_begin, p_end) (group boundaries)
-int group_table(sphb_ctx * c, int p_begin, int p_end, GroupTable & gt)
+int group_table(sphb_ctx * c, int p_begin, int p_end, GroupTable & gt, bool gravity = false)
 {
-    k_group_range<<<1, 32, 0, c->stream>>>(c->grp_start, c->d_ngroups, p_begin, p_end, c->d_grp_ctl); LAUNCH_CHECK();
-    gt.start = c->grp_start; gt.n_groups = c->d_ngroups; gt.ctl = c->d_grp_ctl; gt.n = c->n;
+    const int * start = gravity ? c->grp_start_g : c->grp_start, * ng = gravity ? c->d_ngroups_g : c->d_ngroups;
+    k_group_range<<<1, 32, 0, c->stream>>>(start, ng, p_begin, p_end, c->d_grp_ctl); LAUNCH_CHECK();
+    gt.start = start; gt.n_groups = ng; gt.ctl = c->d_grp_ctl; gt.n = c->n;
     return 0;
 }
 
@@ -485,11 +489,14 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     c->td.n_nodes = n_nodes;
     k_tree_scatter<DIM><<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, c->td, n_nodes, c->d_root); LAUNCH_CHECK();
     // particle groups (sphb_tree.cuh): flags at group starts -> ascending list of starts
-    CK(cudaMemsetAsync(c->grp_flags, 0, (size_t)n, c->stream));
-    k_group_flags<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->world > 1 ? c->slice_groups * 32 : 0, n); LAUNCH_CHECK();
-    {
+    for (int kind = 0; kind < (c->P.use_gravity ? 2 : 1); ++kind) {
+        CK(cudaMemsetAsync(c->grp_flags, 0, (size_t)n, c->stream));
+        k_group_flags<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->world > 1 ? c->slice_groups * 32 : 0, n,
+                                                          kind == 0 ? GROUP_CELL_SPH : GROUP_CELL_GRAV);
+        LAUNCH_CHECK();
         size_t tb = c->cub_tmp_bytes;
-        CK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, thrust::counting_iterator<int>(0), c->grp_flags, c->grp_start, c->d_ngroups, n, c->stream));
+        CK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, thrust::counting_iterator<int>(0), c->grp_flags,
+                                      kind == 0 ? c->grp_start : c->grp_start_g, kind == 0 ? c->d_ngroups : c->d_ngroups_g, n, c->stream));
         ++c->launches;
     }
     c->tree_valid = true;
@@ -630,7 +637,7 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
         k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, c->rc.hsoft, c->n); LAUNCH_CHECK();
         k_grav_leaf_h<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td, c->cur.sml); LAUNCH_CHECK();
         GroupTable gt;
-        if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
+        if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt, true)) return 1;
         const int smem = (int)(4 * sizeof(GravSmem));
 #define SPHB_GRAV(PER, CNT) do { \
             bool & attr_set = c->grav_attr_set[PER ? 1 : 0][CNT ? 1 : 0];      /* per context: the attribute is per device */ \
@@ -786,6 +793,7 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
     cudaMalloc(&q, (SPHB_MAX_LEVELS + 4) * sizeof(int)); c->d_lvl = (int *)q;
     cudaMalloc(&q, 2 * sizeof(int)); c->d_lvl_bad = (int *)q;
     cudaMalloc(&q, sizeof(int)); c->d_ngroups = (int *)q;
+    cudaMalloc(&q, sizeof(int)); c->d_ngroups_g = (int *)q;
     cudaMalloc(&q, 2 * sizeof(int)); c->d_grp_ctl = (int *)q;
     cudaMemset(c->d_scal, 0, 8 * sizeof(double));
     cudaMemset(c->d_err, 0, 4 * sizeof(unsigned long long));
@@ -815,7 +823,7 @@ void sphb_destroy(sphb_ctx * c)
     cudaStreamSynchronize(c->stream);
     if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     free_bag(c->allocs); free_bag(c->node_allocs);
-    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter); cudaFree(c->d_lvl); cudaFree(c->d_lvl_bad); cudaFree(c->d_ngroups); cudaFree(c->d_grp_ctl);
+    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter); cudaFree(c->d_lvl); cudaFree(c->d_lvl_bad); cudaFree(c->d_ngroups); cudaFree(c->d_ngroups_g); cudaFree(c->d_grp_ctl);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->own_stream);

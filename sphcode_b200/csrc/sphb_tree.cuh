@@ -333,18 +333,26 @@ __global__ void k_tree_scatter(TreeBuild t, TreeDev o, int n_nodes, const double
 // A group is the unit of work of every walk kernel: <= 32 consecutive particles of the tree order, one
 // per lane.  Plain 32-particle slices of the sorted order would now and then straddle the boundary of
 // two large cells (consecutive in the key order, far apart in space) and get a huge bounding box, so
-// groups are cut at the boundaries of "group cells": the tree nodes with <= GROUP_CELL_MAX particles
+// groups are cut at the boundaries of "group cells": the tree nodes with <= cell_max particles
 // whose parent has more (and leaves above that size at the maximum level).  A group cell is chopped
-// into slices of 32; every group therefore lies inside one cube holding <= GROUP_CELL_MAX particles.
-constexpr int GROUP_CELL_MAX = 512;
+// into slices of 32; every group therefore lies inside one cube holding <= cell_max particles.
+// The neighbour walks want the cube small (their cost grows with the box + search radius), the gravity walk
+// wants full warps more than a tight box: two group tables are built per tree.
+#ifndef SPHB_GROUP_CELL_SPH
+#define SPHB_GROUP_CELL_SPH 1024
+#endif
+#ifndef SPHB_GROUP_CELL_GRAV
+#define SPHB_GROUP_CELL_GRAV 4096
+#endif
+constexpr int GROUP_CELL_SPH = SPHB_GROUP_CELL_SPH, GROUP_CELL_GRAV = SPHB_GROUP_CELL_GRAV;
 
-__global__ void k_group_flags(TreeBuild t, int n_nodes, unsigned char * __restrict__ flags, int slice_len, int n)
+__global__ void k_group_flags(TreeBuild t, int n_nodes, unsigned char * __restrict__ flags, int slice_len, int n, int cell_max)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     const int cnt = t.count[i];
-    const bool small = cnt <= GROUP_CELL_MAX;
-    const bool parent_big = (i == 0) || t.count[t.parent[i]] > GROUP_CELL_MAX;
+    const bool small = cnt <= cell_max;
+    const bool parent_big = (i == 0) || t.count[t.parent[i]] > cell_max;
     if (!((small && parent_big) || (!small && t.nchild[i] == 0))) return;
     const int first = t.first[i];
     for (int k = 0; k < cnt; k += 32) flags[first + k] = 1;
