@@ -41,6 +41,7 @@ CONFIGS = {
     "evrard_leaf1": ("evrard", dict(N=12, leafParticleNumber=1)),
     "evrard_shallow": ("evrard", dict(N=16, maxTreeLevel=2)),                        # leaves of several hundred particles
     "khi_shallow": ("khi", dict(N=32, maxTreeLevel=3, SPHType="disph")),
+    "khi_gravity_periodic": ("khi", dict(N=32, SPHType="disph", useGravity=True, leafParticleNumber=8)),   # periodic box + tree gravity
 }
 
 

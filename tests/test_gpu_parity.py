@@ -446,3 +446,42 @@ def test_tree_rebuild_after_drastic_change_matches_fresh_context():
     assert np.array_equal(pa["id"], pb["id"])
     np.testing.assert_allclose(pa["phi"], pb["phi"], rtol=1e-12)
     np.testing.assert_allclose(pa["acc"], pb["acc"], rtol=1e-10, atol=1e-12 * np.abs(pb["acc"]).max())
+
+
+def test_gravity_1d_periodic_lattice_error_level():
+    """DIM = 1 tree gravity in the periodic shock tube.  An exact 1-D lattice is the worst case for a
+    per-particle comparison: cell mass centres are exact lattice midpoints, so many opening tests
+    edge^2 > theta^2 d^2 are TIES decided by the last bit of the mass centre (summation order), and with the
+    sample's neighborNumber = 4 the smoothing length converges to exactly two spacings, which puts the
+    neighbours at u = r / (h / 2) = 1 to the last bit, where the reference's softened potential f
+    (src/gravity_force.cpp:21-25: -0.5 where Hernquist & Katz have -2) jumps by 0.35 / e.  The reference differs
+    from itself there under any re-association, so this case is held to BASELINE's gravity criterion instead:
+    the error of the device tree against the direct sum is no worse than the reference tree's."""
+    from sphcode_b200 import sample_params, make_sample
+    from oracle import refsim
+    p = sample_params("shock_tube", N=30, useGravity=True, neighborNumber=5)
+    parts = make_sample(p)
+    c = _ctx(p, parts)
+    c.init_state(); c.make_tree(); c.pre(); c.fluid()
+    fluid = c.particles["acc"].copy()
+    c.gravity()
+    tree = c.particles
+    d = _ctx(p, parts)
+    d.init_state(); d.make_tree(); d.pre(); d.fluid(); d.gravity_direct()
+    direct = d.particles
+    sc_phi = np.abs(direct["phi"]).max()
+    sc_acc = np.abs(direct["acc"] - fluid).max()
+    e_phi = np.abs(tree["phi"] - direct["phi"]) / sc_phi
+    e_acc = np.abs(tree["acc"] - direct["acc"]).max(axis=1) / sc_acc
+    print("device tree vs direct: phi max %.3e median %.3e, acc max %.3e" % (e_phi.max(), np.median(e_phi), e_acc.max()))
+    assert e_phi.max() < 3e-2 and e_acc.max() < 1e-1
+    if refsim.available(1, "tree"):
+        ref = refsim.RefSim(p, parts, 1, "tree")
+        ref.initialize()
+        r = ref.particles
+        U.assert_fields(tree, r, U.PRE_FIELDS, what="1-D gravity case, SPH fields", params=p)
+        r_phi = np.abs(r["phi"] - direct["phi"]) / sc_phi
+        r_acc = np.abs(r["acc"] - direct["acc"]).max(axis=1) / sc_acc
+        print("reference tree vs direct: phi max %.3e median %.3e, acc max %.3e" % (r_phi.max(), np.median(r_phi), r_acc.max()))
+        assert e_phi.max() <= 1.25 * r_phi.max() + 1e-12 and np.median(e_phi) <= 1.25 * np.median(r_phi) + 1e-12
+        assert e_acc.max() <= 1.25 * r_acc.max() + 1e-12
