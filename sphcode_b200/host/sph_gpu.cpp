@@ -12,8 +12,10 @@
 //     outputTime and energies every energyTime in the reference's text formats (src/output.cpp:14-90);
 //     the step itself is sphb_integrate of libsphb.so, the state stays in HBM between outputs.
 // Extensions (do not exist in the reference): `--set key=value` overrides a JSON key (e.g. N,
-// SPHType) without editing the file, `--no-snapshots` keeps only energy.dat, `--steps n` stops after n
-// steps, `--dump-ic file` writes the initial SPHParticle array (binary) and exits without touching a GPU.
+// SPHType) without editing the file, `--no-snapshots` keeps only energy.dat, `--binary-snapshots` writes
+// NNNNN.bin (full-precision SPHParticle records behind a 32-byte header {"SPHB", dim, n, record bytes, time})
+// next to the 6-digit text files, `--steps n` stops after n steps, `--dump-ic file` writes the initial
+// SPHParticle array (binary) and exits without touching a GPU.
 // "threads" is accepted and only used for the host-side generators.
 #include <algorithm>
 #include <chrono>
@@ -551,6 +553,7 @@ struct Output {
     std::string dir;
     std::ofstream energy;
     int count = 0;
+    bool binary = false;
     void open(const std::string & d)
     {
         dir = d;
@@ -577,6 +580,21 @@ struct Output {
                 << r[q.o_scalar(S_ALPHA)] << ' ' << r[q.o_scalar(S_GRADH)] << ' ' << '\n';
         }
         log.line("write " + file);
+        if (binary) {
+            // full-precision snapshot: header + the SPHParticle array as downloaded
+            std::snprintf(name, sizeof(name), "/%05d.bin", count);
+            std::ofstream bin(dir + name, std::ios::binary);
+            const char magic[4] = {'S', 'P', 'H', 'B'};
+            const int32_t dim = q.dim;
+            const int64_t n = (int64_t)q.size(), rec = (int64_t)q.rec;
+            bin.write(magic, 4);
+            bin.write(reinterpret_cast<const char *>(&dim), 4);
+            bin.write(reinterpret_cast<const char *>(&n), 8);
+            bin.write(reinterpret_cast<const char *>(&rec), 8);
+            bin.write(reinterpret_cast<const char *>(&time), 8);
+            bin.write(reinterpret_cast<const char *>(q.bytes.data()), (std::streamsize)q.bytes.size());
+            log.line("write " + dir + name);
+        }
         ++count;
     }
     // src/output.cpp:66-90; the sums run on the device (sphb_energy)
@@ -605,7 +623,7 @@ int main(int argc, char ** argv)
     std::cout << "--------------SPH simulation-------------\n\n";
     std::string target, dump_ic;
     std::vector<std::pair<std::string, std::string>> overrides;
-    bool snapshots = true;
+    bool snapshots = true, binary = false;
     long max_steps = -1;
     int threads = 0, device = 0;
     for (int a = 1; a < argc; ++a) {
@@ -616,6 +634,7 @@ int main(int argc, char ** argv)
             if (eq == std::string::npos) { std::cerr << "--set needs key=value" << std::endl; return EXIT_FAILURE; }
             overrides.emplace_back(kv.substr(0, eq), kv.substr(eq + 1));
         } else if (s == "--no-snapshots") snapshots = false;
+        else if (s == "--binary-snapshots") binary = true;
         else if (s == "--steps" && a + 1 < argc) max_steps = std::atol(argv[++a]);
         else if (s == "--device" && a + 1 < argc) device = std::atoi(argv[++a]);
         else if (s == "--dump-ic" && a + 1 < argc) dump_ic = argv[++a];
@@ -624,7 +643,7 @@ int main(int argc, char ** argv)
     }
     if (target.empty()) {
         std::cerr << "how to use\n" << std::endl;
-        std::cerr << "sph_gpu <paramter.json | sample name> [threads] [--set key=value]... [--no-snapshots] [--steps n] [--device d]" << std::endl;
+        std::cerr << "sph_gpu <paramter.json | sample name> [threads] [--set key=value]... [--no-snapshots] [--binary-snapshots] [--steps n] [--device d]" << std::endl;
         return EXIT_FAILURE;
     }
 #ifdef _OPENMP
@@ -662,6 +681,7 @@ int main(int argc, char ** argv)
         CKB(ctx, sphb_initialize(ctx));                       // Solver::initialize, src/solver.cpp:353-414
 
         Output out;
+        out.binary = binary;
         out.open(run.output_dir);
         double t = run.t_start, t_out = run.t_output, t_ene = run.t_energy;
         if (snapshots) out.particles(ctx, q, t, log);

@@ -340,7 +340,7 @@ def test_cli_run_matches_library(tmp_path):
     assert os.path.exists(exe), "sphcode_b200/host/sph_gpu is missing: run __graft_entry__.build()"
     out = str(tmp_path / "res")
     r = subprocess.run([exe, "evrard", "--set", "N=12", "--set", "endTime=0.05", "--set", "outputTime=0.02",
-                        "--set", f"outputDirectory={out}"], capture_output=True, text=True, timeout=300)
+                        "--set", f"outputDirectory={out}", "--binary-snapshots"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "calclation time" in r.stdout
     p = sample_params("evrard", N=12, endTime=0.05, outputTime=0.02)
@@ -365,6 +365,16 @@ def test_cli_run_matches_library(tmp_path):
     np.testing.assert_allclose(last[:, 0:3], s["pos"], rtol=2e-5, atol=1e-12)
     np.testing.assert_allclose(last[:, 10], s["dens"], rtol=2e-5)
     assert np.array_equal(last[:, 14].astype(int), s["id"]) and np.array_equal(last[:, 15].astype(int), s["neighbor"])
+    # full-precision binary snapshot: 32-byte header + SPHParticle records (the C++ evrard generator and the Python one
+    # differ in the last bit of pow(), hence a tolerance instead of bit equality)
+    raw = open(os.path.join(out, files[-1][:-4] + ".bin"), "rb").read()
+    assert raw[:4] == b"SPHB" and np.frombuffer(raw[4:8], "i4")[0] == 3
+    n_b, rec_b = np.frombuffer(raw[8:24], "i8")
+    assert n_b == len(s) and rec_b == s.dtype.itemsize and len(raw) == 32 + n_b * rec_b
+    snap = np.frombuffer(raw[32:], dtype=s.dtype)
+    for f in ("pos", "vel", "dens", "sml", "phi"):
+        np.testing.assert_allclose(snap[f], s[f], rtol=1e-9, atol=1e-12, err_msg=f)
+    assert np.array_equal(snap["id"], s["id"]) and np.array_equal(snap["neighbor"], s["neighbor"])
 
 
 @pytest.mark.parametrize("sample,over,n_expect", [
