@@ -67,10 +67,6 @@ struct sphb_ctx {
     int n_pad = 0;             // array length (padded for the in-place all-gather)
     PSoA cur{}, alt{};
     std::vector<void *> allocs;            // everything freed at destroy / resize
-    int n_darr = 0, n_iarr = 0;
-    double ** d_ptr_cur = nullptr, ** d_ptr_alt = nullptr;      // device pointer tables for k_permute
-    int ** d_iptr_cur = nullptr, ** d_iptr_alt = nullptr;
-    bool cur_is_a = true;
 
     unsigned long long * keys = nullptr, * keys_alt = nullptr;
     int * idx = nullptr, * idx_alt = nullptr;
@@ -90,7 +86,6 @@ struct sphb_ctx {
     double * d_scal = nullptr;             // [0] dt, [1] h_per_v_sig, [2] dt_force_min, [3..5] energy
     unsigned long long * d_err = nullptr;  // [0] newton non-converged, [1] list overflow, [2] walk error bits
     Counters * d_cnt = nullptr;
-    int * d_group_counter = nullptr;
     double dt = 0.0, hpvs = 0.0;
     bool first_pre = true;
     unsigned long long nonconverged_total = 0;
@@ -188,22 +183,13 @@ int alloc_particles(sphb_ctx * c, int n)
         PSoA & s = side == 0 ? c->cur : c->alt;
         std::vector<double **> d; std::vector<int **> iv;
         list_arrays(c, s, d, iv);
-        c->n_darr = (int)d.size(); c->n_iarr = (int)iv.size();
         double * pool = nullptr; int * ipool = nullptr;
         if (dev_alloc(c, &pool, np * d.size(), c->allocs)) return 1;
         if (dev_alloc(c, &ipool, np * iv.size(), c->allocs)) return 1;
         CK(cudaMemsetAsync(pool, 0, np * d.size() * sizeof(double), c->stream));
         CK(cudaMemsetAsync(ipool, 0, np * iv.size() * sizeof(int), c->stream));
-        std::vector<double *> hp(d.size()); std::vector<int *> hi(iv.size());
-        for (size_t k = 0; k < d.size(); ++k) { *d[k] = pool + k * np; hp[k] = *d[k]; }
-        for (size_t k = 0; k < iv.size(); ++k) { *iv[k] = ipool + k * np; hi[k] = *iv[k]; }
-        double ** dp = nullptr; int ** ip = nullptr;
-        if (dev_alloc(c, &dp, d.size(), c->allocs)) return 1;
-        if (dev_alloc(c, &ip, iv.size(), c->allocs)) return 1;
-        CK(cudaMemcpyAsync(dp, hp.data(), hp.size() * sizeof(double *), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(ip, hi.data(), hi.size() * sizeof(int *), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaStreamSynchronize(c->stream));     // hp / hi go out of scope
-        if (side == 0) { c->d_ptr_cur = dp; c->d_iptr_cur = ip; } else { c->d_ptr_alt = dp; c->d_iptr_alt = ip; }
+        for (size_t k = 0; k < d.size(); ++k) *d[k] = pool + k * np;
+        for (size_t k = 0; k < iv.size(); ++k) *iv[k] = ipool + k * np;
     }
     if (dev_alloc(c, &c->keys, np, c->allocs) || dev_alloc(c, &c->keys_alt, np, c->allocs) ||
         dev_alloc(c, &c->idx, np, c->allocs) || dev_alloc(c, &c->idx_alt, np, c->allocs)) return 1;
@@ -398,8 +384,6 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     LAUNCH_CHECK();
     c->recs_dirty = false;
     std::swap(c->cur, c->alt);
-    std::swap(c->d_ptr_cur, c->d_ptr_alt);
-    std::swap(c->d_iptr_cur, c->d_iptr_alt);
     const unsigned long long * keys = c->keys_alt;
 
     if (c->node_cap == 0) { if (alloc_nodes(c, std::max(1024, n / 2 + 64), 0)) return 1; }
@@ -789,7 +773,6 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
     cudaMalloc(&q, 8 * sizeof(double)); c->d_scal = (double *)q;
     cudaMalloc(&q, 4 * sizeof(unsigned long long)); c->d_err = (unsigned long long *)q;
     cudaMalloc(&q, sizeof(Counters)); c->d_cnt = (Counters *)q;
-    cudaMalloc(&q, sizeof(int)); c->d_group_counter = (int *)q;
     cudaMalloc(&q, (SPHB_MAX_LEVELS + 4) * sizeof(int)); c->d_lvl = (int *)q;
     cudaMalloc(&q, 2 * sizeof(int)); c->d_lvl_bad = (int *)q;
     cudaMalloc(&q, sizeof(int)); c->d_ngroups = (int *)q;
@@ -823,7 +806,7 @@ void sphb_destroy(sphb_ctx * c)
     cudaStreamSynchronize(c->stream);
     if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     free_bag(c->allocs); free_bag(c->node_allocs);
-    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_group_counter); cudaFree(c->d_lvl); cudaFree(c->d_lvl_bad); cudaFree(c->d_ngroups); cudaFree(c->d_ngroups_g); cudaFree(c->d_grp_ctl);
+    cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_lvl); cudaFree(c->d_lvl_bad); cudaFree(c->d_ngroups); cudaFree(c->d_ngroups_g); cudaFree(c->d_grp_ctl);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->own_stream);
