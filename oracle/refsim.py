@@ -135,6 +135,8 @@ def _load(dim, flavour):
         get_vector_array=f("get_vector_array", ci, vp, C.c_char_p, vp),
         kernel_eval=f("kernel_eval", None, vp, vp, cd, vp),
     )
+    if flavour == "port":
+        api["counters"] = f("counters", ci, vp, vp, ci)
     _libs[key] = (L, api)
     return _libs[key]
 
@@ -211,6 +213,18 @@ class RefSim:
     def h_per_v_sig(self): return self._f["get_h_per_v_sig"](self._c)
     @h_per_v_sig.setter
     def h_per_v_sig(self, v): self._f["set_h_per_v_sig"](self._c, float(v))
+
+    COUNTER_NAMES = ("newton_evals", "newton_iters", "pre_candidates", "pre_neighbors", "force_pairs",
+                     "grav_pp", "grav_pc", "grav_node_visits")
+
+    def counters(self, reset=True):
+        """Interaction counts of the reference ALGORITHM since the last reset (port flavour only): the numerators
+        of the algorithmic-FLOP model, same names as sphb_counters."""
+        if "counters" not in self._f:
+            raise RuntimeError("interaction counters exist in the port flavour only")
+        out = np.zeros(8, dtype=np.uint64)
+        self._f["counters"](self._c, out.ctypes.data, int(reset))
+        return dict(zip(self.COUNTER_NAMES, (int(v) for v in out)))
 
     def energy(self):
         out = np.zeros(3)

@@ -83,6 +83,10 @@ typedef struct {
     real dt, time, h_per_v_sig;
     int first_pre;
     real * grad_d, * grad_p, * grad_v[3];    /* GSPH arrays, n*3 each */
+    /* interaction counts of the reference algorithm (the numerators of the algorithmic-FLOP model):
+     * [0] Newton kernel evaluations [1] Newton iterations [2] candidates r2 < h_search^2 [3] neighbours r < h_i
+     * [4] force pairs [5] gravity particle-particle [6] gravity particle-cell [7] gravity node visits */
+    unsigned long long cnt[8];
     char err[256];
 } Ctx;
 
@@ -373,8 +377,9 @@ static real soft_g(real r, real h)
 }
 
 /* BHNode::calc_force, src/bhtree.cpp:301-331 */
-static void node_calc_force(const Ctx * c, const Node * nd, Particle * p_i, real theta2)
+static void node_calc_force(const Ctx * c, const Node * nd, Particle * p_i, real theta2, unsigned long long * k)
 {
+    ++k[2];                                             /* node visit = one opening test */
     const real l2 = nd->edge * nd->edge;
     real d[3];
     calc_r_ij(c, p_i->pos, nd->m_center, d);
@@ -383,6 +388,7 @@ static void node_calc_force(const Ctx * c, const Node * nd, Particle * p_i, real
         if (nd->is_leaf) {
             for (const Particle * p = nd->first; p; p = p->next) {
                 real r_ij[3];
+                ++k[0];
                 calc_r_ij(c, p_i->pos, p->pos, r_ij);
                 const real r = sqrt(abs2v(c, r_ij));
                 p_i->phi -= c->P.G * p->mass * (soft_f(r, p_i->sml) + soft_f(r, p->sml)) * 0.5;
@@ -391,9 +397,10 @@ static void node_calc_force(const Ctx * c, const Node * nd, Particle * p_i, real
             }
         } else {
             for (int i = 0; i < c->nchild; ++i)
-                if (nd->childs[i]) node_calc_force(c, nd->childs[i], p_i, theta2);
+                if (nd->childs[i]) node_calc_force(c, nd->childs[i], p_i, theta2, k);
         }
     } else {
+        ++k[1];
         const real r_inv = 1.0 / sqrt(d2);
         p_i->phi -= c->P.G * nd->mass * r_inv;
         const real s = c->P.G * nd->mass * r_inv * r_inv * r_inv;
@@ -405,7 +412,8 @@ static void node_calc_force(const Ctx * c, const Node * nd, Particle * p_i, real
 static real unit_ball(int dim) { return dim == 1 ? 2.0 : dim == 2 ? M_PI : 4.0 * M_PI / 3.0; }
 
 /* newton_raphson, src/pre_interaction.cpp:227-283 and src/disph/d_pre_interaction.cpp:174-230 */
-static real newton_raphson(const Ctx * c, const Particle * p_i, const int * list, int n_neighbor, real kernel_ratio, int * nonconv)
+static real newton_raphson(const Ctx * c, const Particle * p_i, const int * list, int n_neighbor, real kernel_ratio, int * nonconv,
+                           unsigned long long * evals, unsigned long long * iters)
 {
     const int dim = c->dim, disph = c->P.sph_type == 1;
     real h_i = p_i->sml / kernel_ratio;
@@ -420,9 +428,11 @@ static real newton_raphson(const Ctx * c, const Particle * p_i, const int * list
             calc_r_ij(c, p_i->pos, p_j->pos, r_ij);
             const real r = sqrt(abs2v(c, r_ij));
             if (r >= h_i) break;
+            ++*evals;
             if (disph) { dens += kernel_w(c, r, h_i); ddens += kernel_dhw(c, r, h_i); }
             else { dens += p_j->mass * kernel_w(c, r, h_i); ddens += p_j->mass * kernel_dhw(c, r, h_i); }
         }
+        ++*iters;
         const real f = dens * powh(dim, h_i) - b;
         const real df = ddens * powh(dim, h_i) + dim * dens * powh_(dim, h_i);
         h_i -= f / df;
@@ -477,12 +487,14 @@ static int pre_interaction(Ctx * c, int exhaustive)
         SortItem * tmp = (SortItem *)malloc(sizeof(SortItem) * cap);
         real hpvs_local = DBL_MAX;
         int nonconv = 0;
+        unsigned long long k_ev = 0, k_it = 0, k_cand = 0, k_ngb = 0;
 #pragma omp for
         for (int i = 0; i < c->n; ++i) {
             Particle * p_i = &c->p[i];
             p_i->sml = pow(c->P.neighbor_number * p_i->mass / (p_i->dens * unit_ball(dim)), 1.0 / dim) * kernel_ratio;
             const int n_tmp = neighbor_search(c, p_i->pos, p_i->sml, list, tmp, cap, 0, exhaustive);
-            if (c->P.iterative_sml) p_i->sml = newton_raphson(c, p_i, list, n_tmp, kernel_ratio, &nonconv);
+            k_cand += (unsigned long long)(n_tmp < cap ? n_tmp : cap);
+            if (c->P.iterative_sml) p_i->sml = newton_raphson(c, p_i, list, n_tmp, kernel_ratio, &nonconv, &k_ev, &k_it);
 
             real dens_i = 0.0, dh_dens_i = 0.0, pres_i = 0.0, dh_pres_i = 0.0, n_i = 0.0, dh_n_i = 0.0;
             real v_sig_max = p_i->sound * 2.0;
@@ -495,6 +507,7 @@ static int pre_interaction(Ctx * c, int exhaustive)
                 const real r = sqrt(abs2v(c, r_ij));
                 if (r >= p_i->sml) break;
                 ++n_neighbor;
+                ++k_ngb;
                 const real w_ij = kernel_w(c, r, p_i->sml);
                 dens_i += p_j->mass * w_ij;
                 if (type == 0) {
@@ -595,6 +608,7 @@ static int pre_interaction(Ctx * c, int exhaustive)
         {
             if (hpvs_local < hpvs_min) hpvs_min = hpvs_local;
             nonconv_total += nonconv;
+            c->cnt[0] += k_ev; c->cnt[1] += k_it; c->cnt[2] += k_cand; c->cnt[3] += k_ngb;
         }
         free(list); free(tmp);
     }
@@ -662,6 +676,7 @@ static int fluid_force(Ctx * c, int exhaustive)
     {
         int * list = (int *)malloc(sizeof(int) * cap);
         SortItem * tmp = (SortItem *)malloc(sizeof(SortItem) * cap);
+        unsigned long long k_pairs = 0;
 #pragma omp for
         for (int i = 0; i < c->n; ++i) {
             Particle * p_i = &c->p[i];
@@ -680,6 +695,7 @@ static int fluid_force(Ctx * c, int exhaustive)
                 calc_r_ij(c, p_i->pos, p_j->pos, r_ij);
                 const real r = sqrt(abs2v(c, r_ij));
                 if (r >= (h_i > p_j->sml ? h_i : p_j->sml) || r == 0.0) continue;
+                ++k_pairs;
                 const real cwi = kernel_dwc(c, r, h_i), cwj = kernel_dwc(c, r, p_j->sml);
                 real dw_i[3], dw_j[3], dw_ij[3], v_ij[3];
                 for (int k = 0; k < dim; ++k) {
@@ -753,6 +769,8 @@ static int fluid_force(Ctx * c, int exhaustive)
             for (int k = 0; k < dim; ++k) p_i->acc[k] = acc[k];
             p_i->dene = dene;
         }
+#pragma omp atomic
+        c->cnt[4] += k_pairs;
         free(list); free(tmp);
     }
     return 0;
@@ -780,8 +798,15 @@ static int gravity_force(Ctx * c, int exhaustive)
             for (int k = 0; k < c->dim; ++k) p_i->acc[k] += force[k];
             p_i->phi = phi;
         } else {
+            unsigned long long k[3] = {0, 0, 0};
             p_i->phi = 0.0;                                            /* BHTree::tree_force, src/bhtree.cpp:128-132 */
-            node_calc_force(c, &c->root, p_i, theta2);
+            node_calc_force(c, &c->root, p_i, theta2, k);
+#pragma omp atomic
+            c->cnt[5] += k[0];
+#pragma omp atomic
+            c->cnt[6] += k[1];
+#pragma omp atomic
+            c->cnt[7] += k[2];
         }
     }
     return 0;
@@ -988,6 +1013,14 @@ long long spho_neighbor_search_all(void * v, const double * h, int is_ij, long l
     offsets[c->n] = tot;
     free(list); free(tmp);
     return tot;
+}
+
+/* interaction counts since the last reset (see Ctx::cnt) */
+int spho_counters(void * v, unsigned long long * out, int reset)
+{
+    Ctx * c = (Ctx *)v;
+    for (int k = 0; k < 8; ++k) { out[k] = c->cnt[k]; if (reset) c->cnt[k] = 0; }
+    return 0;
 }
 
 int spho_get_vector_array(void * v, const char * name, double * out)

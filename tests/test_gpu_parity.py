@@ -495,3 +495,25 @@ def test_gravity_1d_periodic_lattice_error_level():
         print("reference tree vs direct: phi max %.3e median %.3e, acc max %.3e" % (r_phi.max(), np.median(r_phi), r_acc.max()))
         assert e_phi.max() <= 1.25 * r_phi.max() + 1e-12 and np.median(e_phi) <= 1.25 * np.median(r_phi) + 1e-12
         assert e_acc.max() <= 1.25 * r_acc.max() + 1e-12
+
+
+@pytest.mark.parametrize("name", ["evrard_c4", "evrard_n30", "khi_disph_ac", "gresho_gsph2"])
+def test_interaction_counts_equal_the_reference_algorithm(name):
+    """The device's interaction counters (the numerators of bench.py's algorithmic-FLOP figures) against the counts
+    of the reference ALGORITHM taken by the C port on the same input: candidates, neighbours, Newton evaluations
+    and iterations, force pairs, gravity particle-particle / particle-cell interactions and node visits must be
+    EQUAL — the device does the reference's interactions, no more and no fewer."""
+    from oracle import refsim
+    p, parts = U.make_case(name)
+    c = _ctx(p, parts)
+    c.initialize()
+    c.enable_counters(True)
+    c.integrate()
+    kd = c.counters()
+    sim = refsim.RefSim(p, parts, p["DIM"], "port")
+    sim.initialize()
+    sim.counters()
+    sim.integrate()
+    kr = sim.counters()
+    diff = {k: (kd[k], kr[k]) for k in kr if kd[k] != kr[k]}
+    assert not diff, diff

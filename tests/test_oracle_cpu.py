@@ -144,3 +144,27 @@ def test_port_energy_history_matches_golden(name):
     ge, gdt = g[name + "_energy"], g[name + "_dt"]
     assert np.abs(e - ge).max() <= 1e-9 * np.abs(ge).max()
     assert (np.abs(dts - gdt) / gdt).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["evrard_c4", "khi_disph_ac", "shock_tube_c1"])
+def test_port_interaction_counters_are_consistent(name):
+    """The port counts the interactions of the reference ALGORITHM (the numerators of the algorithmic-FLOP model,
+    SURVEY.md 8d).  Self-consistency: the neighbour counter equals the sum of SPHParticle::neighbor, force pairs
+    come in (i, j) / (j, i) twins, every Newton iteration evaluates at least the particle itself, and with gravity
+    every particle visits the root and meets itself."""
+    p, parts = U.make_case(name)
+    sim = RefSim(p, parts, p["DIM"], "port")
+    sim.initialize()
+    sim.counters()
+    sim.integrate()
+    k = sim.counters()
+    n = len(parts)
+    assert k["pre_neighbors"] == int(sim.particles["neighbor"].sum())
+    assert k["force_pairs"] % 2 == 0 and k["force_pairs"] > 0
+    assert k["pre_candidates"] >= k["pre_neighbors"] >= n
+    assert k["newton_iters"] >= n and k["newton_evals"] >= k["newton_iters"]
+    if p["useGravity"]:
+        assert k["grav_node_visits"] >= n and k["grav_pp"] >= n and k["grav_pc"] > 0
+    else:
+        assert k["grav_node_visits"] == k["grav_pp"] == k["grav_pc"] == 0
+    assert sim.counters() == dict.fromkeys(RefSim.COUNTER_NAMES, 0)          # reset
