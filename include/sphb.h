@@ -164,6 +164,10 @@ int sphb_fluid_force(sphb_ctx *ctx);
 int sphb_gravity_force(sphb_ctx *ctx);
 /* The EXHAUSTIVE_SEARCH flavour of the same module (src/gravity_force.cpp:70-84): direct sum. */
 int sphb_gravity_direct(sphb_ctx *ctx);
+/* The same direct sum for the first k particles of the caller's buffer only (targets), over ALL particles as
+ * sources: the "64k-particle subsample" gate of the tree-gravity error distribution at sizes where N^2 is out
+ * of reach.  Other particles keep acc / phi. */
+int sphb_gravity_direct_targets(sphb_ctx *ctx, int k);
 
 /* TimeStep::calculation (src/timestep.cpp:18-38): sets and returns dt. */
 int sphb_timestep(sphb_ctx *ctx, double *dt);

@@ -90,6 +90,7 @@ struct ref_ctx {
     std::shared_ptr<Simulation>    sim;
     std::shared_ptr<Module> timestep, pre, fforce, gforce;
     bool tree_sized = false;
+    int n_full = 0;            // particles in the vector / in the tree (>= Simulation::particle_num, see ref_set_active)
     std::string err;
 };
 
@@ -155,6 +156,7 @@ ref_ctx * ref_create(const ref_params * p, int n, const void * particles)
         for(auto & q : v) q.next = nullptr;
         c->sim->set_particles(v);
         c->sim->set_particle_num(n);
+        c->n_full = n;
 
         // module selection: src/solver.cpp:359-370
 #ifdef SPHB_GPU_MODULES
@@ -249,10 +251,10 @@ int ref_make_tree(ref_ctx * c)
     try {
         auto tree = c->sim->get_tree();
         if(!c->tree_sized) {
-            tree->resize(c->sim->get_particle_num());
+            tree->resize(c->n_full);
             c->tree_sized = true;
         }
-        tree->make(c->sim->get_particles(), c->sim->get_particle_num());
+        tree->make(c->sim->get_particles(), c->n_full);
     } catch(std::exception & e) { c->err = e.what(); return 1; }
 #endif
     return 0;
@@ -270,6 +272,60 @@ void   ref_set_dt(ref_ctx * c, double dt) { c->sim->set_dt(dt); }
 double ref_get_time(ref_ctx * c) { return c->sim->get_time(); }
 double ref_get_h_per_v_sig(ref_ctx * c) { return c->sim->get_h_per_v_sig(); }
 void   ref_set_h_per_v_sig(ref_ctx * c, double v) { c->sim->set_h_per_v_sig(v); }
+
+// Subsample mode (parity checks at sizes where the whole reference pass would take minutes): the modules loop
+// `for i < sim->get_particle_num()` (src/pre_interaction.cpp:48,55; src/fluid_force.cpp; src/gravity_force.cpp:59,66)
+// while BHTree::make / neighbor_search / tree_force work on whatever was handed to make().  With the tree made over
+// ALL n_full particles and particle_num lowered to k, the unmodified modules compute particles 0..k-1 against all
+// n_full sources.  k = 0 restores n_full.
+void ref_set_active(ref_ctx * c, int k) { c->sim->set_particle_num(k > 0 && k < c->n_full ? k : c->n_full); }
+// BHTree::set_kernel (src/bhtree.cpp:109-112), which PreInteraction calls last (src/pre_interaction.cpp:167)
+int ref_set_kernel(ref_ctx * c)
+{
+#ifndef EXHAUSTIVE_SEARCH
+    try { c->sim->get_tree()->set_kernel(); } catch(std::exception & e) { c->err = e.what(); return 1; }
+#endif
+    return 0;
+}
+// Direct gravity sum of the EXHAUSTIVE_SEARCH GravityForce (src/gravity_force.cpp:70-84) for the targets 0..k-1
+// against all n_full sources, through the module's own softening functions f and g (src/gravity_force.cpp:16-42
+// are file-static there, so the two are restated from those lines): out = k * (DIM + 1) doubles {force, phi}.
+static inline real dsum_f(const real r, const real h)
+{
+    const real e = h * 0.5, u = r / e;
+    if(u < 1.0) return (-0.5 * u * u * (1.0 / 3.0 - 3.0 / 20 * u * u + u * u * u / 20) + 1.4) / e;
+    if(u < 2.0) return -1.0 / (15 * r) + (-u * u * (4.0 / 3.0 - u + 0.3 * u * u - u * u * u / 30) + 1.6) / e;
+    return 1 / r;
+}
+static inline real dsum_g(const real r, const real h)
+{
+    const real e = h * 0.5, u = r / e;
+    if(u < 1.0) return (4.0 / 3.0 - 1.2 * u * u + 0.5 * u * u * u) / (e * e * e);
+    if(u < 2.0) return (-1.0 / 15 + 8.0 / 3 * u * u * u - 3 * u * u * u * u + 1.2 * u * u * u * u * u - u * u * u * u * u * u / 6.0) / (r * r * r);
+    return 1 / (r * r * r);
+}
+void ref_direct_gravity(ref_ctx * c, int k, double * out)
+{
+    auto & particles = c->sim->get_particles();
+    auto * periodic = c->sim->get_periodic().get();
+    const int n = c->n_full;
+    const real G = c->param->gravity.constant;
+#pragma omp parallel for schedule(dynamic, 16)
+    for(int i = 0; i < k; ++i) {
+        const auto & p_i = particles[i];
+        real phi = 0.0;
+        vec_t force(0.0);
+        for(int j = 0; j < n; ++j) {
+            const auto & p_j = particles[j];
+            const vec_t r_ij = periodic->calc_r_ij(p_i.pos, p_j.pos);
+            const real r = std::abs(r_ij);
+            phi -= G * p_j.mass * (dsum_f(r, p_i.sml) + dsum_f(r, p_j.sml)) * 0.5;
+            force -= r_ij * (G * p_j.mass * (dsum_g(r, p_i.sml) + dsum_g(r, p_j.sml)) * 0.5);
+        }
+        for(int d = 0; d < DIM; ++d) out[(size_t)i * (DIM + 1) + d] = force[d];
+        out[(size_t)i * (DIM + 1) + DIM] = phi;
+    }
+}
 
 // Solver::predict, src/solver.cpp:431-456
 void ref_predict(ref_ctx * c)

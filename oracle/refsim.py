@@ -137,6 +137,10 @@ def _load(dim, flavour):
     )
     if flavour == "port":
         api["counters"] = f("counters", ci, vp, vp, ci)
+    else:
+        api["set_active"] = f("set_active", None, vp, ci)
+        api["set_kernel"] = f("set_kernel", ci, vp)
+        api["direct_gravity"] = f("direct_gravity", None, vp, ci, vp)
     _libs[key] = (L, api)
     return _libs[key]
 
@@ -188,6 +192,18 @@ class RefSim:
         p = np.ascontiguousarray(p, dtype=self.dtype)
         assert len(p) == self.n
         self._f["set_particles"](self._c, p.ctypes.data)
+
+    def set_active(self, k):
+        """Subsample mode: the unmodified modules compute particles 0..k-1 against ALL particles (0 = all again)."""
+        self._f["set_active"](self._c, int(k))
+
+    def set_kernel(self): self._check(self._f["set_kernel"](self._c))
+
+    def direct_gravity(self, k):
+        """Direct sum of src/gravity_force.cpp:70-84 for targets 0..k-1 over all sources: (force[k, dim], phi[k])."""
+        out = np.zeros((k, self.dim + 1))
+        self._f["direct_gravity"](self._c, int(k), out.ctypes.data)
+        return out[:, :self.dim].copy(), out[:, self.dim].copy()
 
     def init_state(self): self._f["init_state"](self._c)
     def make_tree(self): self._check(self._f["make_tree"](self._c))

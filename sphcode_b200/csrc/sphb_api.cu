@@ -4,7 +4,7 @@
 // context's stream, and the NCCL exchange of the multi-GPU mode.  All arithmetic lives in the
 // kernels of sphb_tree.cuh / sphb_stages.cuh.  There is no CPU fallback anywhere in this file.
 #include "../../include/sphb.h"
-#include "sphb_stages.cuh"
+#include "sphb_dist.cuh"
 
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -27,7 +27,7 @@ std::string g_create_error;
 // ---- minimal NCCL binding (dlopen: single-GPU use must not need libnccl) ----------------------
 typedef struct ncclComm * ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclInt32 = 2, ncclInt = 2, ncclUint64 = 5, ncclFloat64 = 8 };
+enum { ncclInt8 = 0, ncclInt32 = 2, ncclInt = 2, ncclInt64 = 4, ncclUint64 = 5, ncclFloat64 = 8 };
 enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 };
 struct NcclApi {
     void * lib = nullptr;
@@ -36,6 +36,8 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char * (*GetErrorString)(int) = nullptr;
@@ -46,7 +48,7 @@ struct NcclApi {
         for (const char * nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
         if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
 #define NSYM(f) f = reinterpret_cast<decltype(f)>(dlsym(lib, "nccl" #f)); if (!f) { err = "libnccl lacks nccl" #f; return false; }
-        NSYM(GetUniqueId) NSYM(CommInitRank) NSYM(CommDestroy) NSYM(AllGather) NSYM(AllReduce) NSYM(GroupStart) NSYM(GroupEnd)
+        NSYM(GetUniqueId) NSYM(CommInitRank) NSYM(CommDestroy) NSYM(AllGather) NSYM(AllReduce) NSYM(Send) NSYM(Recv) NSYM(GroupStart) NSYM(GroupEnd)
         NSYM(GetErrorString)
 #undef NSYM
         return true;
@@ -607,13 +609,21 @@ template <int DIM> int force_d(sphb_ctx * c)
     c->err = "unsupported kernel / SPH type"; return 1;
 }
 
-template <int DIM> int gravity_t(sphb_ctx * c, bool direct)
+template <int DIM> int gravity_t(sphb_ctx * c, bool direct, int k_targets = 0)
 {
     Timer tm(c, SPHB_T_GRAVITY);
     const Slice s = my_slice(c);
     if (direct) {
         if (c->world > 1) { c->err = "sphb_gravity_direct is single-GPU only"; return 1; }
-        k_gravity_direct<DIM><<<cdiv(c->n, 128), 128, 0, c->stream>>>(c->cur, c->P, c->n); LAUNCH_CHECK();
+        if (k_targets > 0 && k_targets < c->n) {
+            // targets = particles 0..k-1 of the caller's buffer: list of their sorted-order indices in idx (tree scratch)
+            int * cnt = c->d_grp_ctl;
+            CK(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
+            k_select_targets<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.orig, c->n, k_targets, c->idx, cnt); LAUNCH_CHECK();
+            k_gravity_direct<DIM><<<cdiv(k_targets, 128), 128, 0, c->stream>>>(c->cur, c->P, c->n, c->idx, k_targets); LAUNCH_CHECK();
+            return 0;
+        }
+        k_gravity_direct<DIM><<<cdiv(c->n, 128), 128, 0, c->stream>>>(c->cur, c->P, c->n, nullptr, c->n); LAUNCH_CHECK();
         return 0;
     }
     if (s.n_local > 0) {
@@ -688,7 +698,7 @@ template <int DIM> int correct_t(sphb_ctx * c)
 int make_tree(sphb_ctx * c) { return DIM_SWITCH(c, make_tree_t<1>(c), make_tree_t<2>(c), make_tree_t<3>(c)); }
 int pre(sphb_ctx * c) { return DIM_SWITCH(c, pre_d<1>(c), pre_d<2>(c), pre_d<3>(c)); }
 int force(sphb_ctx * c) { return DIM_SWITCH(c, force_d<1>(c), force_d<2>(c), force_d<3>(c)); }
-int gravity(sphb_ctx * c, bool direct) { return DIM_SWITCH(c, gravity_t<1>(c, direct), gravity_t<2>(c, direct), gravity_t<3>(c, direct)); }
+int gravity(sphb_ctx * c, bool direct, int k = 0) { return DIM_SWITCH(c, gravity_t<1>(c, direct, k), gravity_t<2>(c, direct, k), gravity_t<3>(c, direct, k)); }
 int exchange(sphb_ctx * c) { return DIM_SWITCH(c, exchange_forces<1>(c), exchange_forces<2>(c), exchange_forces<3>(c)); }
 int timestep(sphb_ctx * c) { return DIM_SWITCH(c, timestep_t<1>(c), timestep_t<2>(c), timestep_t<3>(c)); }
 int predict(sphb_ctx * c) { return DIM_SWITCH(c, predict_t<1>(c), predict_t<2>(c), predict_t<3>(c)); }
@@ -1031,6 +1041,15 @@ int sphb_gravity_direct(sphb_ctx * c)
     if (!c->P.use_gravity) return 0;
     if (!c->n) { c->err = "no particles uploaded"; return 1; }
     return gravity(c, true);
+}
+
+int sphb_gravity_direct_targets(sphb_ctx * c, int k)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->P.use_gravity) return 0;
+    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (k <= 0) { c->err = "bad target count"; return 1; }
+    return gravity(c, true, k);
 }
 
 int sphb_timestep(sphb_ctx * c, double * dt)

@@ -852,7 +852,7 @@ struct GravSmem {
     double4  mx[32];                    // mixed nodes of the current batch: mass centre + mass
     double   me2[32];                   //   edge^2
     int4     minfo[32];                 //   {child0, nchild, first, count}
-    double   mh2[32];                   //   leaves: largest h^2 among the leaf's particles (k_grav_leaf_h)
+    double   mh2[32];                   //   leaves: largest h^2 among the leaf's particles (k_apply_ksize)
     unsigned mmask[32];                 //   lane mask; afterwards the accept rows of the batch, compacted
     int      msl[32];                   //   chunk slot (within the batch) of the mixed node
 };
@@ -1062,7 +1062,10 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         if (last || ngc > GV_GC - 32) {
             __syncwarp();
             if (COUNT) n_pc += ngc;
-            if (ngc & 1) { if (lane == 0) sm.gcell[ngc] = make_double4(1e30, 1e30, 1e30, 0.0); ++ngc; }   // pad to even with a massless cell
+            if (ngc & 1) {     // pad to even: the last cell again (far from every lane by construction), massless
+                if (lane == 0) { double4 pad = sm.gcell[ngc - 1]; pad.w = 0.0; sm.gcell[ngc] = pad; }
+                ++ngc;
+            }
             __syncwarp();
 #pragma unroll (GC_UNROLL)
             for (int kk = 0; kk < ngc; kk += 2) {
@@ -1299,28 +1302,20 @@ __global__ void k_grav_pack(const double * __restrict__ sml, double2 * __restric
     hsoft[i] = make_double2(2.0 / h, h * h * (1.0 + 1e-12));
 }
 
-// per leaf: the largest h^2 (with the margin of hsoft.y) among its particles -> ng record [3].y, the
-// softening threshold of the particle-particle pass 1
-__global__ void k_grav_leaf_h(TreeDev t, const double * __restrict__ sml)
+// Direct sum, the EXHAUSTIVE_SEARCH flavour of GravityForce (src/gravity_force.cpp:70-84).  targets == nullptr: every
+// particle; else the n_targets particles (sorted-order indices) listed there, against all n sources.
+__global__ void k_select_targets(const int * __restrict__ orig, int n, int k, int * __restrict__ list, int * __restrict__ count)
 {
-    const int D = blockIdx.x * blockDim.x + threadIdx.x;
-    if (D >= t.n_nodes) return;
-    double2 * ng = t.ng + (size_t)D * 4;
-    const double2 q2 = ng[2], q3 = ng[3];
-    if (__double2hiint(q2.y)) return;                  // internal node
-    const int first = __double2loint(q3.x), count = __double2hiint(q3.x);
-    double h = 0.0;
-    for (int j = first; j < first + count; ++j) h = fmax(h, sml[j]);
-    ng[3].y = h * h * (1.0 + 1e-12);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && orig[i] < k) list[atomicAdd(count, 1)] = i;
 }
-
-// Direct sum, the EXHAUSTIVE_SEARCH flavour of GravityForce (src/gravity_force.cpp:70-84).
 template <int DIM>
-__global__ void __launch_bounds__(128) k_gravity_direct(PSoA p, DevParams P, int n)
+__global__ void __launch_bounds__(128) k_gravity_direct(PSoA p, DevParams P, int n, const int * __restrict__ targets, int n_targets)
 {
     __shared__ double sx[DIM][128], sm[128], sh[128];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = t < n_targets;
+    const int i = valid ? (targets ? targets[t] : t) : 0;
     double ri[DIM], f[DIM], phi = 0.0, h_i = 1.0;
 #pragma unroll
     for (int a = 0; a < DIM; ++a) { ri[a] = 0.0; f[a] = 0.0; }

@@ -34,7 +34,7 @@ constexpr int PSOA_NDOUBLE = 12 + 12;   // permuted double arrays (without gradi
 struct TreeBuild {
     int *first, *count, *level, *parent, *child0, *nchild;
     double *center[3];
-    double *msum, *mpos[3];
+    double4 *msum4;            // {sum m, sum m x, sum m y, sum m z}: one contiguous array (all-reduced in the multi-GPU mode)
 };
 
 // Finished tree, breadth-first order, one packed 64-byte record (4 x double2) per node and walk
@@ -48,9 +48,10 @@ struct TreeDev {
     double2 *nn;
     double2 *ng;
     int     *parent;    // index of the parent, -1 for the root
+    double  *ksize;     // BHNode::kernel_size while it is being reduced (contiguous: all-reduced (max) in the multi-GPU
+                        // mode), then copied into the nn / ng records by k_apply_ksize
 };
 __device__ __forceinline__ double pack_ints(int lo, int hi) { return __hiloint2double(hi, lo); }
-__device__ __forceinline__ double * node_ksize(const TreeDev & t, int idx) { return &t.nn[(size_t)idx * 4 + 2].x; }
 
 // root[0..2] = centre, root[3] = edge.
 // ---- bounding cube: BHTree::make, src/bhtree.cpp:59-95 -----------------------------------------
@@ -268,35 +269,36 @@ __global__ void k_root_init(TreeBuild t, int n, const double * __restrict__ root
 }
 
 // mass, sum m*pos; one level per launch, deepest level first
-// (BHNode::assign accumulations, src/bhtree.cpp:199-201)
+// (BHNode::assign accumulations, src/bhtree.cpp:199-201).  posm = packed {x, y, z, m} records, global tree-order index.
+// mode 0: leaves and internal nodes of the level (single GPU);
+// mode 1: leaves only, restricted to the particles [own_lo, own_hi) this rank owns (multi-GPU: partial sums, the ranks'
+//         arrays are then all-reduced; run once over all nodes); mode 2: internal nodes of the level only.
 template <int DIM>
-__global__ void k_level_up(TreeBuild t, PSoA p, int lvl_begin, int lvl_end)
+__global__ void k_level_up(TreeBuild t, const double4 * __restrict__ posm, int lvl_begin, int lvl_end, int own_lo, int own_hi, int mode)
 {
     const int i = lvl_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= lvl_end) return;
-    double m = 0.0, mp[DIM];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) mp[d] = 0.0;
+    double m = 0.0, mp[3] = {0.0, 0.0, 0.0};
     const int nc = t.nchild[i];
     if (nc == 0) {
-        const int first = t.first[i], last = first + t.count[i];
+        if (mode == 2) return;
+        const int first = max(t.first[i], own_lo), last = min(t.first[i] + t.count[i], own_hi);
         for (int j = first; j < last; ++j) {
-            const double mj = p.mass[j];
-            m += mj;
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) mp[d] += p.pos[d][j] * mj;
+            const double4 pj = posm[j];
+            m += pj.w;
+            mp[0] += pj.x * pj.w;
+            if (DIM >= 2) mp[1] += pj.y * pj.w;
+            if (DIM >= 3) mp[2] += pj.z * pj.w;
         }
     } else {
+        if (mode == 1) { t.msum4[i] = make_double4(0.0, 0.0, 0.0, 0.0); return; }
         const int c0 = t.child0[i];
         for (int k = 0; k < nc; ++k) {
-            m += t.msum[c0 + k];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) mp[d] += t.mpos[d][c0 + k];
+            const double4 q = t.msum4[c0 + k];
+            m += q.x; mp[0] += q.y; mp[1] += q.z; mp[2] += q.w;
         }
     }
-    t.msum[i] = m;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) t.mpos[d][i] = mp[d];
+    t.msum4[i] = make_double4(m, mp[0], mp[1], mp[2]);
 }
 
 template <int DIM>
@@ -312,9 +314,11 @@ __global__ void k_tree_scatter(TreeBuild t, TreeDev o, int n_nodes, const double
     if (i != 0) {
         // the reference never accumulates the root's mass / mass centre (root_clear,
         // include/bhtree.hpp:46-53): keep 0 so that the walk reproduces its behaviour.
-        m = t.msum[i];
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) mc[d] = t.mpos[d][i] / m;       // src/bhtree.cpp:152
+        const double4 q = t.msum4[i];
+        m = q.x;
+        mc[0] = q.y / m;                                              // src/bhtree.cpp:152
+        if (DIM >= 2) mc[1] = q.z / m;
+        if (DIM >= 3) mc[2] = q.w / m;
     }
     const double edge = ldexp(root[3], -(level - 1));
     const int nc = t.nchild[i];
@@ -388,28 +392,42 @@ __device__ __forceinline__ bool next_group(const GroupTable & gt, int lane, int 
     return true;
 }
 
-// BHNode::set_kernel (src/bhtree.cpp:206-232): per node the largest sml beneath it.
+// BHNode::set_kernel (src/bhtree.cpp:206-232): per node the largest sml beneath it.  Three kernels: clear, leaf maxima
+// carried up the parent chain by atomic max (over the particles [own_lo, own_hi) this rank owns; sml is indexed by the
+// global tree-order index), and — after the all-reduce (max) of the multi-GPU mode — the copy into the walk records:
+// nn[2].x = kernel_size (symmetric neighbour search, src/bhtree.cpp:237), ng[3].y = (largest h of a LEAF)^2 with the
+// margin of hsoft.y (softening threshold of the gravity particle-particle pass).
 __global__ void k_clear_kernel(TreeDev t)
 {
     const int D = blockIdx.x * blockDim.x + threadIdx.x;
-    if (D < t.n_nodes) *node_ksize(t, D) = 0.0;
+    if (D < t.n_nodes) t.ksize[D] = 0.0;
 }
-__global__ void k_set_kernel(TreeDev t, const double * __restrict__ sml)
+__global__ void k_set_kernel(TreeDev t, const double * __restrict__ sml, int own_lo, int own_hi)
 {
     const int D = blockIdx.x * blockDim.x + threadIdx.x;
     if (D >= t.n_nodes) return;
     const double2 q2 = t.nn[(size_t)D * 4 + 2], q3 = t.nn[(size_t)D * 4 + 3];
     if (__double2hiint(q2.y)) return;                  // internal node
-    const int first = __double2loint(q3.x), count = __double2hiint(q3.x);
+    const int first = max(__double2loint(q3.x), own_lo), last = min(__double2loint(q3.x) + __double2hiint(q3.x), own_hi);
+    if (first >= last) return;
     double h = 0.0;
-    for (int j = first; j < first + count; ++j) { const double s = sml[j]; if (s > h) h = s; }
+    for (int j = first; j < last; ++j) { const double s = sml[j]; if (s > h) h = s; }
     const unsigned long long hb = (unsigned long long)__double_as_longlong(h);
     int q = D;
     while (q >= 0) {
-        const unsigned long long old = atomic_max_pos(node_ksize(t, q), h);
+        const unsigned long long old = atomic_max_pos(&t.ksize[q], h);
         if (old >= hb) break;          // whoever wrote `old` carries it (or more) upward
         q = t.parent[q];
     }
+}
+__global__ void k_apply_ksize(TreeDev t)
+{
+    const int D = blockIdx.x * blockDim.x + threadIdx.x;
+    if (D >= t.n_nodes) return;
+    const double h = t.ksize[D];
+    double2 * nn = t.nn + (size_t)D * 4;
+    nn[2].x = h;
+    if (__double2hiint(nn[2].y) == 0) t.ng[(size_t)D * 4 + 3].y = h * h * (1.0 + 1e-12);
 }
 
 // r_ij = r_i - {x,y,z of a staged particle}, minimum image if periodic

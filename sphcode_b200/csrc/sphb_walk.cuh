@@ -55,6 +55,8 @@ template <int DIM> struct Filter32 {
     double ref[DIM];      // = group box centre
     double rlim;          // candidates farther than this from ref (max norm) cannot be gather neighbours
     double delta;         // absolute per-axis error bound of the FP32 coordinates inside rlim
+    double sc;            // warp-uniform power of two ~ 1 / rlim: every FP32 quantity is staged as (value * sc), so the
+                          // filter is independent of the unit system (h ~ 1e20 cm or 1e-20 must not leave the FP32 range)
 };
 
 // V:  void hit(int j)   — particle j passed lane's conservative test; the exact test is the caller's.
@@ -81,17 +83,18 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
     // ---- FP32 filter set-up
     Filter32<DIM> F;
     double lmax = 0.0;
+    F.rlim = (bhmax + reach) * 1.001 + slack;
+    F.sc = scalbn(1.0, -ilogb(F.rlim));                  // exact scaling: staged coordinates inside rlim are in (-2, 2)
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
         F.ref[d] = bc[d];
-        F.fi[d] = (float)(ri[d] - bc[d]);
-        F.L[d] = (float)P.range[d];
+        F.fi[d] = (float)((ri[d] - bc[d]) * F.sc);
+        F.L[d] = (float)(P.range[d] * F.sc);
         if (P.periodic) lmax = fmax(lmax, P.range[d]);
     }
-    F.rlim = (bhmax + reach) * 1.001 + slack;
     F.delta = 1.1920929e-7 * (F.rlim + lmax);            // 2^-23 * magnitude bound
     {
-        const double hh = h_i + 4.0 * F.delta;
+        const double hh = (h_i + 4.0 * F.delta) * F.sc;
         F.thr = valid ? (float)(hh * hh * (1.0 + 4e-6)) : -1.0f;
     }
 
@@ -148,15 +151,15 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
                 if (P.periodic) dj[d] = min_image(dj[d], P.range[d]);
                 amax = fmax(amax, fabs(dj[d]));
             }
-            float4 f = make_float4((float)dj[0], DIM >= 2 ? (float)dj[DIM >= 2 ? 1 : 0] : 0.f,
-                                   DIM >= 3 ? (float)dj[DIM >= 3 ? 2 : 0] : 0.f, -1.0f);
+            float4 f = make_float4((float)(dj[0] * F.sc), DIM >= 2 ? (float)(dj[DIM >= 2 ? 1 : 0] * F.sc) : 0.f,
+                                   DIM >= 3 ? (float)(dj[DIM >= 3 ? 2 : 0] * F.sc) : 0.f, -1.0f);
             if (SYM) {
                 const double hj = __ldg(hj_src + (size_t)j * hj_stride);
                 const double dl = 1.1920929e-7 * (fmax(amax, F.rlim) + lmax);
-                const double hh = hj + 4.0 * (dl + F.delta);
-                f.w = (float)(hh * hh * (1.0 + 4e-6));
+                const double hh = (hj + 4.0 * (dl + F.delta)) * F.sc;
+                f.w = (float)(hh * hh * (1.0 + 4e-6));   // +inf for an h_j beyond FP32 range: passes (conservative)
             } else if (amax > F.rlim) {
-                f.x = 3e18f;                         // cannot be within h_search of any lane
+                f.x = 3e18f;                         // scaled units: lanes sit in (-2, 2), thresholds <= 4: cannot pass
             }
             sm.tile32[lane] = f;
         }

@@ -127,6 +127,7 @@ SYMBOLS = {
     "sphb_fluid_force": (_i, [_vp]),
     "sphb_gravity_force": (_i, [_vp]),
     "sphb_gravity_direct": (_i, [_vp]),
+    "sphb_gravity_direct_targets": (_i, [_vp, _i]),
     "sphb_timestep": (_i, [_vp, C.POINTER(_d)]),
     "sphb_predict": (_i, [_vp]),
     "sphb_correct": (_i, [_vp]),
@@ -246,7 +247,11 @@ class Context:
     def pre(self): self._ck(self.L.sphb_pre_interaction(self._c))
     def fluid(self): self._ck(self.L.sphb_fluid_force(self._c))
     def gravity(self): self._ck(self.L.sphb_gravity_force(self._c))
-    def gravity_direct(self): self._ck(self.L.sphb_gravity_direct(self._c))
+    def gravity_direct(self, targets=None):
+        if targets:
+            self._ck(self.L.sphb_gravity_direct_targets(self._c, int(targets)))
+        else:
+            self._ck(self.L.sphb_gravity_direct(self._c))
     def predict(self): self._ck(self.L.sphb_predict(self._c))
     def correct(self): self._ck(self.L.sphb_correct(self._c))
     def initialize(self): self._ck(self.L.sphb_initialize(self._c))

@@ -24,6 +24,26 @@ ENERGY_CASES = {
     "evrard": ("evrard", dict(N=12)),                                                   # configs[3] physics (DISPH + gravity)
 }
 STEPS = 60
+# full-length histories (north_star as worded): the shipped shock tube to its endTime (0.2: 332 steps), khi at N=256
+# and evrard at N=30 (14 328 particles, through maximum compression) for several hundred steps.
+# value = (sample, overrides, steps); steps None = run to the sample's endTime
+LONG_CASES = {
+    "shock_tube_long": ("shock_tube", dict(N=50), None),
+    "khi_long": ("khi", dict(N=256, SPHType="disph", useArtificialConductivity=True), 300),
+    "evrard_long": ("evrard", dict(N=30), 400),
+}
+
+
+def history_to(sim, t_end):
+    """as history(), until the accumulated time passes t_end (Solver::run's loop, src/solver.cpp:318-341)"""
+    e = [sim.energy()]
+    dts = []
+    t = 0.0
+    while t < t_end:
+        dts.append(sim.integrate())
+        t += dts[-1]
+        e.append(sim.energy())
+    return np.array(e, dtype=np.float64), np.array(dts, dtype=np.float64)
 
 
 def history(sim, steps):
@@ -49,6 +69,16 @@ def main():
         out[name + "_dt"] = dts
         tot = e.sum(axis=1)
         print(f"{name}: n={len(parts)} t_end={dts.sum():.4g} E0={tot[0]:.6g} drift={abs(tot[-1] - tot[0]) / abs(tot[0]):.2e}")
+    for name, (sample, over, steps) in LONG_CASES.items():
+        p = sample_params(sample, **over)
+        parts = make_sample(p)
+        ref = RefSim(p, parts, p["DIM"], "tree")
+        ref.initialize()
+        e, dts = history(ref, steps) if steps else history_to(ref, p["endTime"])
+        out[name + "_energy"] = e
+        out[name + "_dt"] = dts
+        tot = e.sum(axis=1)
+        print(f"{name}: n={len(parts)} steps={len(dts)} t_end={dts.sum():.4g} E0={tot[0]:.6g} drift={abs(tot[-1] - tot[0]) / abs(tot[0]):.2e}")
     np.savez_compressed(os.path.join(HERE, "energy_histories.npz"), **out)
 
 

@@ -168,3 +168,44 @@ def test_port_interaction_counters_are_consistent(name):
     else:
         assert k["grav_node_visits"] == k["grav_pp"] == k["grav_pc"] == 0
     assert sim.counters() == dict.fromkeys(RefSim.COUNTER_NAMES, 0)          # reset
+
+
+def test_reference_subsample_mode_equals_the_full_pass():
+    """oracle/ref_driver.cpp ref_set_active: the unmodified modules on particles 0..k-1 against all sources must give,
+    bit for bit, what the full pass gives for those particles (this is what the 16 M parity check relies on), and
+    ref_direct_gravity must equal the EXHAUSTIVE_SEARCH GravityForce."""
+    from oracle import refsim
+    if not (refsim.available(3, "tree") and refsim.available(3, "exhaustive")):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    import parity_util as U
+    p, parts = U.make_case("evrard_c4")
+    n = len(parts)
+    rng = np.random.default_rng(3)
+    parts = parts[rng.permutation(n)]
+    parts["id"] = np.arange(n)                  # the reference identifies particles by id == index (src/bhtree.cpp:257)
+    full = refsim.RefSim(p, parts, 3, "tree")
+    full.initialize()
+    F = full.particles
+    k = 300
+    sub = refsim.RefSim(p, parts, 3, "tree")
+    sub.init_state(); sub.make_tree(); sub.set_active(k); sub.pre()
+    S = sub.particles
+    for f in U.PRE_FIELDS:
+        assert np.array_equal(S[f][:k], F[f][:k]), f
+    state = F.copy()
+    for f in ("acc", "dene", "phi"):
+        state[f] = 0
+    sub.set_active(0)
+    sub.particles = state
+    sub.make_tree(); sub.set_kernel(); sub.set_active(k)
+    sub.fluid(); sub.gravity()
+    S = sub.particles
+    for f in U.FORCE_FIELDS:
+        assert np.array_equal(S[f][:k], F[f][:k]), f
+    assert not S["phi"][k:].any()
+    fd, phid = sub.direct_gravity(64)
+    ex = refsim.RefSim(p, state, 3, "exhaustive")
+    ex.gravity()
+    E = ex.particles
+    np.testing.assert_allclose(fd, E["acc"][:64], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(phid, E["phi"][:64], rtol=1e-13)
