@@ -82,13 +82,22 @@ const char *sphb_last_error(const sphb_ctx *ctx);   /* ctx may be NULL: last cre
 int sphb_set_stream(sphb_ctx *ctx, void *cuda_stream);
 int sphb_synchronize(sphb_ctx *ctx);
 int sphb_dim(const sphb_ctx *ctx);
-int sphb_particle_num(const sphb_ctx *ctx);
+int sphb_particle_num(const sphb_ctx *ctx);           /* particles THIS rank holds (all of them on one GPU) */
+long long sphb_global_particle_num(const sphb_ctx *ctx);  /* particles of the whole job */
+long long sphb_first_global_index(const sphb_ctx *ctx);   /* tree-order index of this rank's first particle */
 size_t sphb_sizeof_particle(int dim);
 
-/* Multi-GPU: make this context rank `rank` of `world` contexts that share one particle set.
- * `nccl_comm` is an ncclComm_t created by the caller (one per rank).  After this call
- * sphb_upload_aos takes the GLOBAL particle set on every rank; each rank computes a contiguous
- * Morton-curve slice of it and the stage calls exchange what the other ranks need. */
+/* Multi-GPU (one process per GPU, all GPUs on one NVLink box): make this context rank `rank` of `world` contexts that
+ * together hold ONE particle set, split by Morton-curve domain decomposition.  `nccl_comm` is an ncclComm_t created
+ * by the caller (one per rank).  After this call
+ *   - sphb_upload_aos takes the rank's SHARE of the particles (any split of the global set; ids are the caller's);
+ *     the first tree build ships every particle to the rank that owns its key range and re-balances every step;
+ *   - a rank keeps the full state of its own particles only; what it needs of others (ghost particles within reach of
+ *     its h, leaves its gravity walk opens) it reads from the owners' memory over NVLink (CUDA IPC peer mappings);
+ *     tree topology, node masses / mass centres and kernel sizes are global (NCCL all-reduce), dt is all-reduced (min);
+ *   - every stage call below is collective; sphb_particle_num() is the rank's current count, sphb_download_aos
+ *     returns the rank's current particles in its tree order (and an upload with that count updates them in place);
+ *   - GSPH, sphb_neighbor_lists, sphb_gravity_direct and the vector-array calls are single-GPU only. */
 int sphb_set_distributed(sphb_ctx *ctx, int rank, int world, void *nccl_comm);
 /* Same, but the library creates (and owns) the communicator: rank 0 calls sphb_nccl_unique_id,
  * ships the 128 bytes to the other ranks by any means (MPI, torch.distributed, a file), and every
@@ -122,9 +131,11 @@ int sphb_set_distributed_id(sphb_ctx *ctx, int rank, int world, const void *uniq
 /* Host AoS -> device.  First call (or a different n) sizes the context (BHTree::resize,
  * src/bhtree.cpp:42-53).  `stride` = bytes between records (>= sphb_sizeof_particle(dim)).
  * field_mask selects which members are taken from the host copy; the first upload must
- * use SPHB_F_ALL. */
+ * use SPHB_F_ALL.  With a partial mask and a pinned / registered host buffer (sphb_host_alloc,
+ * cudaHostRegister) the selected members are read in place over PCIe — nothing else moves. */
 int sphb_upload_aos(sphb_ctx *ctx, const void *particles, int n, size_t stride, uint32_t field_mask);
-/* Device -> host AoS; only members in field_mask are written. */
+/* Device -> host AoS; only members in field_mask are written (pinned / registered buffer and a
+ * partial mask: written in place over PCIe by the pack kernel, no staging and no host pass). */
 int sphb_download_aos(sphb_ctx *ctx, void *particles, int n, size_t stride, uint32_t field_mask);
 
 /* GSPH MUSCL gradient arrays, Simulation::get_vector_array(name) (src/simulation.cpp:68-76):
@@ -230,6 +241,9 @@ int sphb_get_timers(sphb_ctx *ctx, float ms[SPHB_T_COUNT]);
 
 /* Number of kernel launches issued by this context since creation. */
 uint64_t sphb_launch_count(const sphb_ctx *ctx);
+/* Multi-GPU bookkeeping since creation: ghost records read from peers / particles shipped to other ranks. */
+uint64_t sphb_halo_records(const sphb_ctx *ctx);
+uint64_t sphb_migrated(const sphb_ctx *ctx);
 /* Particles whose Newton-Raphson smoothing-length iteration did not converge since creation (the
  * reference only logs "Particle id N is not convergence", src/pre_interaction.cpp:277-280, and
  * falls back to the guess; so does the device). */

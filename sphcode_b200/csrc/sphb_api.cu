@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
 
 using namespace sphb;
@@ -57,6 +59,8 @@ struct NcclApi {
 
 } // namespace
 
+constexpr int SPHB_TSEG = 8;             // event pairs per timer kind between two reads (a stage may run several phases)
+
 struct sphb_ctx {
     int dim = 0, device = 0;
     sphb_params hp{};
@@ -65,12 +69,17 @@ struct sphb_ctx {
     cudaStream_t own_stream = nullptr;   // created by sphb_create, destroyed by sphb_destroy
     int sm_count = 148;
 
-    int n = 0;                 // particles
-    int n_pad = 0;             // array length (padded for the in-place all-gather)
-    PSoA cur{}, alt{};
+    int n = 0;                 // particles this rank owns (= all particles on a single GPU)
+    int n_glob = 0;            // particles of the whole job (tree, keys and gather records are global)
+    int off = 0;               // global tree-order index of the first own particle
+    int cap = 0;               // length of the state arrays (own particles + room for arrivals)
+    int n_rec = 0;             // length of the gather-record arrays (n_glob, padded)
+    PSoA cur{}, alt{};         // state of the own particles, local index
+    PSoA gv{};                 // "global view" of cur: pointers shifted by -off, valid for indices [off, off + n)
     std::vector<void *> allocs;            // everything freed at destroy / resize
 
-    unsigned long long * keys = nullptr, * keys_alt = nullptr;
+    unsigned long long * keys = nullptr, * keys_alt = nullptr;   // local keys / sorted local keys (keys_alt lives in the slab)
+    unsigned long long * keys_glob = nullptr;                    // multi-GPU: all ranks' sorted keys (single GPU: = keys_alt)
     int * idx = nullptr, * idx_alt = nullptr;
     void * cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
 
@@ -82,26 +91,28 @@ struct sphb_ctx {
     bool force_full_sort = false;          // redo of a tree build whose partial key sort was too shallow
     int * d_lvl = nullptr, * d_lvl_bad = nullptr;   // speculative tree build: level bounds / failure flag on the device
     bool tree_valid = false;
+    bool ksize_valid = false;              // node kernel sizes (nn[2].x, ng[3].y) match the current sml
+    bool hsoft_valid = false;              // gravity softening records match the current sml and tree order
 
     double * d_root = nullptr;             // centre[3], edge
     double * d_bbox_part = nullptr; int bbox_blocks = 0;
-    double * d_scal = nullptr;             // [0] dt, [1] h_per_v_sig, [2] dt_force_min, [3..5] energy
-    unsigned long long * d_err = nullptr;  // [0] newton non-converged, [1] list overflow, [2] walk error bits
+    double * d_scal = nullptr;             // [0] dt, [1] h_per_v_sig, [2] dt_force_min, [3..5] energy, [8..13] -lo / hi of the bounding box
+    unsigned long long * d_err = nullptr;  // [0] newton non-converged, [1] list overflow, [2] walk error bits, [3] halo records pulled
     Counters * d_cnt = nullptr;
     double dt = 0.0, hpvs = 0.0;
     bool first_pre = true;
     unsigned long long nonconverged_total = 0;
 
     double * scratch_r = nullptr, * scratch_m = nullptr; int * scratch_j = nullptr; int pre_grid = 0, grav_grid = 0;
-    unsigned char * grp_flags = nullptr;   // 1 where a group starts (tree order)
-    int * grp_start = nullptr;             // first particle of every group, ascending (neighbour walks)
+    unsigned char * grp_flags = nullptr;   // 1 where a group starts (own particles, local index)
+    int * grp_start = nullptr;             // first particle (global index) of every group, ascending (neighbour walks)
     int * d_ngroups = nullptr;             // number of groups (device)
     int * grp_start_g = nullptr;           // the same for the gravity walk (larger group cells)
     int * d_ngroups_g = nullptr;
     int * d_grp_ctl = nullptr;             // [0] work counter, [1] end group of the current kernel
     double2 * grav_lq = nullptr; int * grav_near = nullptr;   // per-warp leaf queues / softened-pair lists of the gravity walk
     bool grav_attr_set[2][2] = {{false, false}, {false, false}};   // dynamic-smem attribute set for k_gravity<DIM, PER, CNT>
-    Recs rc{};                             // packed gather records (tree order)
+    Recs rc{};                             // packed gather records, GLOBAL tree-order index (inside the slab)
     bool recs_dirty = true;                // SoA fields changed since the records were packed
 
     void * d_aos = nullptr; size_t d_aos_bytes = 0;
@@ -110,15 +121,27 @@ struct sphb_ctx {
     bool counters_on = false, timers_on = false;
     sphb_counters last_counters{};
     int last_ngroups = 0;
-    cudaEvent_t ev[2 * SPHB_T_COUNT] = {};
+    cudaEvent_t ev[SPHB_T_COUNT][SPHB_TSEG][2] = {};
+    int nseg[SPHB_T_COUNT] = {};
     float ms[SPHB_T_COUNT] = {};
-    bool ev_used[SPHB_T_COUNT] = {};
     uint64_t launches = 0;
 
-    // multi-GPU
+    // ---- multi-GPU: Morton domain decomposition (sphb_dist.cuh)
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr; bool own_comm = false;
-    int slice_groups = 0;                  // groups of 32 particles per rank
+    std::vector<int> n_all, off_all;       // every rank's particle count / first global index (off_all has world + 1 entries)
+    char * slab = nullptr; size_t slab_bytes = 0; SlabLayout lay{};
+    std::vector<void *> peer_open;         // IPC mappings to close
+    PeerTab pt{};
+    unsigned long long * d_split = nullptr; bool split_valid = false;
+    int * d_mig = nullptr;                 // [world + 1] leavers per destination + total, [world] cursors, [world] send offsets, [world * world] all ranks' counts
+    int * mig_idx = nullptr, * mig_dest = nullptr;
+    double * mig_send = nullptr, * mig_recv = nullptr;
+    int * cells_s = nullptr, * cells_g = nullptr, * d_ncells = nullptr;   // group cells overlapping the own range ([0] SPH, [1] gravity)
+    unsigned char * halo_flags = nullptr, * halo_have = nullptr;
+    int * d_bar = nullptr;
+    bool orig_valid = true;                // `orig` is a permutation of the caller's buffer indices (false once particles migrated)
+    uint64_t halo_pulled = 0, migrated = 0;
 
     std::string err;
 };
@@ -136,11 +159,26 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 size_t rec_size(int dim) { return (size_t)(4 * dim + 12) * 8 + 16; }
 
+// One timed phase of kind k: every phase between two reads gets its own event pair and the read sums them (a stage
+// can have several phases of a kind, e.g. the exchange steps of one time step).
 struct Timer {
-    sphb_ctx * c; int k;
-    Timer(sphb_ctx * c_, int k_) : c(c_), k(k_) { if (c->timers_on) cudaEventRecord(c->ev[2 * k], c->stream); }
-    ~Timer() { if (c->timers_on) { cudaEventRecord(c->ev[2 * k + 1], c->stream); c->ev_used[k] = true; } }
+    sphb_ctx * c; int k, seg;
+    Timer(sphb_ctx * c_, int k_) : c(c_), k(k_), seg(-1)
+    {
+        if (c->timers_on && c->nseg[k] < SPHB_TSEG) { seg = c->nseg[k]++; cudaEventRecord(c->ev[k][seg][0], c->stream); }
+    }
+    ~Timer() { if (seg >= 0) cudaEventRecord(c->ev[k][seg][1], c->stream); }
 };
+void read_timers(sphb_ctx * c)
+{
+    for (int k = 0; k < SPHB_T_COUNT; ++k) {
+        if (!c->nseg[k]) continue;
+        float tot = 0.f;
+        for (int s = 0; s < c->nseg[k]; ++s) { float m = 0.f; cudaEventElapsedTime(&m, c->ev[k][s][0], c->ev[k][s][1]); tot += m; }
+        c->ms[k] = tot;
+        c->nseg[k] = 0;
+    }
+}
 
 template <class T> int dev_alloc(sphb_ctx * c, T ** p, size_t count, std::vector<void *> & bag)
 {
@@ -171,15 +209,95 @@ void list_arrays(sphb_ctx * c, PSoA & s, std::vector<double **> & d, std::vector
     i.push_back(&s.pid); i.push_back(&s.neighbor); i.push_back(&s.orig);
 }
 
-int alloc_particles(sphb_ctx * c, int n)
+// gv = cur with every pointer shifted by -off: the walk kernels index particles by their global tree-order index
+void make_global_view(sphb_ctx * c)
 {
+    c->gv = c->cur;
+    std::vector<double **> d; std::vector<int **> iv;
+    list_arrays(c, c->gv, d, iv);
+    for (double ** q : d) *q -= c->off;
+    for (int ** q : iv) *q -= c->off;
+}
+
+int nccl_barrier(sphb_ctx * c)
+{
+    if (c->world == 1) return 0;
+    CKN(g_nccl.AllReduce(c->d_bar, c->d_bar, 1, ncclInt32, ncclSum, c->comm, c->stream));
+    return 0;
+}
+
+void close_peers(sphb_ctx * c)
+{
+    for (void * q : c->peer_open) cudaIpcCloseMemHandle(q);
+    c->peer_open.clear();
+}
+
+// exchange the IPC handle of the record slab: every rank maps every other rank's slab
+int open_peers(sphb_ctx * c)
+{
+    close_peers(c);
+    c->pt = PeerTab{};
+    c->pt.world = c->world; c->pt.rank = c->rank;
+    c->pt.slab[c->rank] = c->slab;
+    if (c->world == 1) return 0;
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, c->slab));
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    char * d_h = nullptr;
+    CK(cudaMalloc(&d_h, sizeof(mine) * c->world));
+    CK(cudaMemcpyAsync(d_h + sizeof(mine) * c->rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+    CKN(g_nccl.AllGather(d_h + sizeof(mine) * c->rank, d_h, sizeof(mine), ncclInt8, c->comm, c->stream));
+    CK(cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * c->world, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_h);
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) continue;
+        void * q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            c->err = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e) +
+                     " — the multi-GPU mode needs all ranks on one box with peer access (every GPU visible to every process)";
+            return 1;
+        }
+        c->peer_open.push_back(q);
+        c->pt.slab[r] = static_cast<const char *>(q);
+    }
+    return 0;
+}
+
+// n_up = particles this rank was handed; sizes everything for the job
+int alloc_particles(sphb_ctx * c, int n_up)
+{
+    close_peers(c);
     free_bag(c->allocs);
     c->cur = PSoA{}; c->alt = PSoA{};
-    c->n = n;
-    const int groups = cdiv(n, 32);
-    c->slice_groups = cdiv(groups, c->world);
-    c->n_pad = c->slice_groups * c->world * 32;
-    const size_t np = (size_t)c->n_pad;
+    c->n = n_up;
+    c->n_all.assign(c->world, n_up);
+    c->off_all.assign(c->world + 1, 0);
+    long long ng = n_up;
+    if (c->world > 1) {
+        if (c->world > MAX_WORLD) { c->err = "world size above MAX_WORLD"; return 1; }
+        if (c->P.sph_type == T_GSPH) { c->err = "GSPH is single-GPU only (the MUSCL gradient arrays are not part of the halo records)"; return 1; }
+        // every rank's count
+        int * d_n = nullptr;
+        CK(cudaMalloc(&d_n, sizeof(int) * c->world));
+        CK(cudaMemcpyAsync(d_n + c->rank, &n_up, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CKN(g_nccl.AllGather(d_n + c->rank, d_n, 1, ncclInt32, c->comm, c->stream));
+        CK(cudaMemcpyAsync(c->n_all.data(), d_n, sizeof(int) * c->world, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(d_n);
+        ng = 0;
+        for (int r = 0; r < c->world; ++r) { c->off_all[r] = (int)ng; ng += c->n_all[r]; }
+        if (ng > 2000000000LL) { c->err = "more than 2e9 particles"; return 1; }
+    }
+    c->off_all[c->world] = (int)ng;
+    c->off = c->off_all[c->rank];
+    c->n_glob = (int)ng;
+    const int n_max = *std::max_element(c->n_all.begin(), c->n_all.end());
+    c->cap = c->world == 1 ? n_up : std::max<long long>(n_max, (long long)(ng / c->world * 1.3) + 4096) + 32;
+    c->n_rec = c->n_glob + 64;
+    const size_t np = (size_t)c->cap;
+    const int n = c->cap;
 
     for (int side = 0; side < 2; ++side) {
         PSoA & s = side == 0 ? c->cur : c->alt;
@@ -193,20 +311,37 @@ int alloc_particles(sphb_ctx * c, int n)
         for (size_t k = 0; k < d.size(); ++k) *d[k] = pool + k * np;
         for (size_t k = 0; k < iv.size(); ++k) *iv[k] = ipool + k * np;
     }
-    if (dev_alloc(c, &c->keys, np, c->allocs) || dev_alloc(c, &c->keys_alt, np, c->allocs) ||
-        dev_alloc(c, &c->idx, np, c->allocs) || dev_alloc(c, &c->idx_alt, np, c->allocs)) return 1;
+    // record slab (exported to the peers): posm | velc | thermo | av | hsoft | sorted local keys
+    {
+        const size_t nr = (size_t)c->n_rec;
+        SlabLayout & L = c->lay;
+        L.posm = 0; L.velc = nr * 32; L.thermo = nr * 64; L.av = nr * 96; L.hsoft = nr * 128; L.keys = nr * 144;
+        c->slab_bytes = L.keys + (np + 32) * sizeof(unsigned long long);
+        if (dev_alloc(c, &c->slab, c->slab_bytes, c->allocs)) return 1;
+        CK(cudaMemsetAsync(c->slab, 0, c->slab_bytes, c->stream));
+        c->rc.posm = reinterpret_cast<double4 *>(c->slab + L.posm); c->rc.velc = reinterpret_cast<double4 *>(c->slab + L.velc);
+        c->rc.thermo = reinterpret_cast<double4 *>(c->slab + L.thermo); c->rc.av = reinterpret_cast<double4 *>(c->slab + L.av);
+        c->rc.hsoft = reinterpret_cast<double2 *>(c->slab + L.hsoft);
+        c->keys_alt = reinterpret_cast<unsigned long long *>(c->slab + L.keys);
+    }
+    if (dev_alloc(c, &c->keys, np, c->allocs) || dev_alloc(c, &c->idx, np, c->allocs) || dev_alloc(c, &c->idx_alt, np, c->allocs)) return 1;
+    if (c->world > 1) { if (dev_alloc(c, &c->keys_glob, (size_t)c->n_glob + 32, c->allocs)) return 1; }
+    else c->keys_glob = c->keys_alt;
     c->cub_tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, c->cub_tmp_bytes, c->keys, c->keys_alt, c->idx, c->idx_alt, n, 0, 64, c->stream);
     size_t scan_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int *)nullptr, (int *)nullptr, 5 * n + 2, c->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int *)nullptr, (int *)nullptr, (int)std::min<long long>(5LL * c->n_glob + 2, 2000000000LL), c->stream);
     size_t sel_bytes = 0;
     cub::DeviceSelect::Flagged(nullptr, sel_bytes, thrust::counting_iterator<int>(0), (unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, n, c->stream);
-    c->cub_tmp_bytes = std::max(std::max(c->cub_tmp_bytes, scan_bytes), sel_bytes) + 256;
+    size_t keysort_bytes = 0;
+    if (c->world > 1) cub::DeviceRadixSort::SortKeys(nullptr, keysort_bytes, c->keys_glob, c->keys_glob, c->n_glob, 0, 64, c->stream);
+    c->cub_tmp_bytes = std::max(std::max(std::max(c->cub_tmp_bytes, scan_bytes), sel_bytes), keysort_bytes) + 256;
     { char * t = nullptr; if (dev_alloc(c, &t, c->cub_tmp_bytes, c->allocs)) return 1; c->cub_tmp = t; }
     c->bbox_blocks = std::min(cdiv(n, 256), 4 * c->sm_count);
     if (dev_alloc(c, &c->d_bbox_part, (size_t)c->bbox_blocks * 6, c->allocs)) return 1;
 
     // list scratch: one r, j (and m) column set per resident warp of the persistent pre / force kernels
+    const int groups = cdiv(n, 32);
     c->pre_grid = std::min(cdiv(groups, 4), c->sm_count * PF_BLOCKS);
     c->grav_grid = std::min(cdiv(groups, 4), c->sm_count * GV_BLOCKS);
     const size_t slots = (size_t)c->pre_grid * 4;
@@ -219,16 +354,29 @@ int alloc_particles(sphb_ctx * c, int n)
     if (c->P.use_gravity) {
         if (dev_alloc(c, &c->grav_lq, slots * GRAV_LQ * 32, c->allocs) || dev_alloc(c, &c->grav_near, slots * GRAV_NEAR * 32, c->allocs)) return 1;
     }
-    // packed gather records
-    if (dev_alloc(c, &c->rc.posm, np, c->allocs) || dev_alloc(c, &c->rc.velc, np, c->allocs) ||
-        dev_alloc(c, &c->rc.thermo, np, c->allocs) || dev_alloc(c, &c->rc.av, np, c->allocs) ||
-        dev_alloc(c, &c->rc.hsoft, np, c->allocs)) return 1;
     c->recs_dirty = true;
 
     c->d_aos_bytes = (size_t)n * rec_size(c->dim);
     { char * t = nullptr; if (dev_alloc(c, &t, c->d_aos_bytes, c->allocs)) return 1; c->d_aos = t; }
-    c->tree_valid = false;
+    if (c->world > 1) {
+        const int W = c->world;
+        if (dev_alloc(c, &c->d_split, W + 1, c->allocs) || dev_alloc(c, &c->d_mig, 3 * W + 1 + W * W, c->allocs) ||
+            dev_alloc(c, &c->mig_idx, np, c->allocs) || dev_alloc(c, &c->mig_dest, np, c->allocs) ||
+            dev_alloc(c, &c->mig_send, np * mig_rec(c->dim), c->allocs) || dev_alloc(c, &c->mig_recv, np * mig_rec(c->dim), c->allocs) ||
+            dev_alloc(c, &c->cells_s, np + 32, c->allocs) || dev_alloc(c, &c->cells_g, np + 32, c->allocs) ||
+            dev_alloc(c, &c->d_ncells, 2, c->allocs) || dev_alloc(c, &c->d_bar, 1, c->allocs)) return 1;
+        CK(cudaMemsetAsync(c->d_bar, 0, sizeof(int), c->stream));
+        if (open_peers(c)) return 1;
+    } else {
+        c->pt = PeerTab{}; c->pt.world = 1; c->pt.slab[0] = c->slab;
+    }
+    for (int r = 0; r <= c->world; ++r) c->pt.off[r] = c->off_all[r];
+    c->split_valid = false;
+    c->orig_valid = true;
+    c->tree_valid = false; c->ksize_valid = false; c->hsoft_valid = false;
     c->first_pre = true;
+    c->levels.clear();
+    make_global_view(c);
     return 0;
 }
 
@@ -251,14 +399,16 @@ int alloc_nodes(sphb_ctx * c, int cap, int keep, int keep_offs = 0)
     for (int d = 0; d < c->dim; ++d) {
         if (dev_alloc(c, &t.center[d], cap, c->node_allocs)) return 1;
         if (keep) CK(cudaMemcpyAsync(t.center[d], old.center[d], (size_t)keep * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        if (dev_alloc(c, &t.mpos[d], cap, c->node_allocs)) return 1;
     }
-    if (dev_alloc(c, &t.msum, cap, c->node_allocs)) return 1;
+    if (dev_alloc(c, &t.msum4, cap, c->node_allocs)) return 1;
     if (dev_alloc(c, &c->lvl_tmp, cap, c->node_allocs) || dev_alloc(c, &c->lvl_offs, cap, c->node_allocs)) return 1;
     if (keep_offs) CK(cudaMemcpyAsync(c->lvl_offs, old_offs, (size_t)keep_offs * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     TreeDev & o = c->td;
     if (dev_alloc(c, &o.nn, (size_t)cap * 4, c->node_allocs) || dev_alloc(c, &o.ng, (size_t)cap * 4, c->node_allocs) ||
-        dev_alloc(c, &o.parent, cap, c->node_allocs)) return 1;
+        dev_alloc(c, &o.parent, cap, c->node_allocs) || dev_alloc(c, &o.ksize, cap, c->node_allocs)) return 1;
+    if (c->world > 1) {
+        if (dev_alloc(c, &c->halo_flags, (size_t)cap + 8, c->node_allocs) || dev_alloc(c, &c->halo_have, (size_t)cap + 8, c->node_allocs)) return 1;
+    }
     CK(cudaStreamSynchronize(c->stream));
     free_bag(old_bag);
     c->node_cap = cap;
@@ -299,8 +449,10 @@ __global__ void k_unpack(const char * __restrict__ aos, size_t stride, PSoA s, i
     if (mask & SPHB_F_NEIGHBOR) s.neighbor[i] = iq[1];
 }
 
+// SoA -> the caller's AoS order.  Only the members in `mask` are written (a full mask also nulls SPHParticle::next), so
+// the same kernel serves the staged full download and a field-masked download straight into mapped host memory.
 template <int DIM>
-__global__ void k_pack(char * __restrict__ aos, size_t stride, PSoA s, int n)
+__global__ void k_pack(char * __restrict__ aos, size_t stride, PSoA s, int n, uint32_t mask)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -308,14 +460,28 @@ __global__ void k_pack(char * __restrict__ aos, size_t stride, PSoA s, int n)
     double * r = reinterpret_cast<double *>(aos + (size_t)k * stride);
 #pragma unroll
     for (int d = 0; d < DIM; ++d) {
-        r[d] = s.pos[d][i]; r[DIM + d] = s.vel[d][i]; r[2 * DIM + d] = s.vel_p[d][i]; r[3 * DIM + d] = s.acc[d][i];
+        if (mask & SPHB_F_POS)   r[d] = s.pos[d][i];
+        if (mask & SPHB_F_VEL)   r[DIM + d] = s.vel[d][i];
+        if (mask & SPHB_F_VEL_P) r[2 * DIM + d] = s.vel_p[d][i];
+        if (mask & SPHB_F_ACC)   r[3 * DIM + d] = s.acc[d][i];
     }
     double * q = r + 4 * DIM;
-    q[0] = s.mass[i]; q[1] = s.dens[i]; q[2] = s.pres[i]; q[3] = s.ene[i]; q[4] = s.ene_p[i]; q[5] = s.dene[i];
-    q[6] = s.sml[i]; q[7] = s.sound[i]; q[8] = s.balsara[i]; q[9] = s.alpha[i]; q[10] = s.gradh[i]; q[11] = s.phi[i];
+    if (mask & SPHB_F_MASS)    q[0] = s.mass[i];
+    if (mask & SPHB_F_DENS)    q[1] = s.dens[i];
+    if (mask & SPHB_F_PRES)    q[2] = s.pres[i];
+    if (mask & SPHB_F_ENE)     q[3] = s.ene[i];
+    if (mask & SPHB_F_ENE_P)   q[4] = s.ene_p[i];
+    if (mask & SPHB_F_DENE)    q[5] = s.dene[i];
+    if (mask & SPHB_F_SML)     q[6] = s.sml[i];
+    if (mask & SPHB_F_SOUND)   q[7] = s.sound[i];
+    if (mask & SPHB_F_BALSARA) q[8] = s.balsara[i];
+    if (mask & SPHB_F_ALPHA)   q[9] = s.alpha[i];
+    if (mask & SPHB_F_GRADH)   q[10] = s.gradh[i];
+    if (mask & SPHB_F_PHI)     q[11] = s.phi[i];
     int * iq = reinterpret_cast<int *>(q + 12);
-    iq[0] = s.pid[i]; iq[1] = s.neighbor[i];
-    q[13] = 0.0;       // SPHParticle::next: tree scratch in the reference, null here
+    if (mask & SPHB_F_ID)       iq[0] = s.pid[i];
+    if (mask & SPHB_F_NEIGHBOR) iq[1] = s.neighbor[i];
+    if ((mask & SPHB_F_ALL) == SPHB_F_ALL) q[13] = 0.0;       // SPHParticle::next: tree scratch in the reference, null here
 }
 
 __global__ void k_scatter_by_orig(const double * __restrict__ src, const int * __restrict__ orig, double * __restrict__ dst, int n, int ncomp, int comp)
@@ -334,41 +500,140 @@ __global__ void k_set_scalars(double * s, double dt, double hpvs, int which)
     if (which & 2) s[1] = hpvs;
 }
 
-// (re)pack the gather records from the SoA state: what = 1 posm | 2 velc | 4 thermo + av
+// (re)pack the gather records of the own particles from the SoA state: what = 1 posm | 2 velc | 4 thermo + av
 int pack_recs(sphb_ctx * c, int what)
 {
     const int n = c->n, B = 256;
-    switch (c->dim) {
-    case 1: k_pack_recs<1><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what); break;
-    case 2: k_pack_recs<2><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what); break;
-    default: k_pack_recs<3><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what); break;
+    if (n > 0) {
+        switch (c->dim) {
+        case 1: k_pack_recs<1><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what, c->off); break;
+        case 2: k_pack_recs<2><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what, c->off); break;
+        default: k_pack_recs<3><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->rc, n, what, c->off); break;
+        }
+        LAUNCH_CHECK();
     }
-    LAUNCH_CHECK();
     if (what == 7) c->recs_dirty = false;
     return 0;
 }
 int ensure_recs(sphb_ctx * c) { return c->recs_dirty ? pack_recs(c, 7) : 0; }
 
-// group table view for a kernel that works on the particles [p_begin, p_end) (group boundaries)
-int group_table(sphb_ctx * c, int p_begin, int p_end, GroupTable & gt, bool gravity = false)
+// group table view for a kernel that works on the own particles
+int group_table(sphb_ctx * c, GroupTable & gt, bool gravity = false)
 {
     const int * start = gravity ? c->grp_start_g : c->grp_start, * ng = gravity ? c->d_ngroups_g : c->d_ngroups;
-    k_group_range<<<1, 32, 0, c->stream>>>(start, ng, p_begin, p_end, c->d_grp_ctl); LAUNCH_CHECK();
-    gt.start = start; gt.n_groups = ng; gt.ctl = c->d_grp_ctl; gt.n = c->n;
+    k_group_range<<<1, 32, 0, c->stream>>>(start, ng, c->off, c->off + c->n, c->d_grp_ctl); LAUNCH_CHECK();
+    gt.start = start; gt.n_groups = ng; gt.ctl = c->d_grp_ctl; gt.n = c->off + c->n;
     return 0;
+}
+
+// ---- multi-GPU: particle migration to the owners of their keys ------------------------------------------------------------
+// On entry c->keys holds the keys of the n own particles (local order).  Particles whose key lies outside this rank's
+// splitter range are shipped to their owner (ncclSend / ncclRecv of packed records), arrivals are appended behind the
+// own particles, and the leavers' keys get the leaver bit, so that the sort moves them behind everything that stays.
+// *n_sort = entries to sort, *n_new = particles this rank owns afterwards.
+template <int DIM> int migrate_t(sphb_ctx * c, int * n_sort, int * n_new)
+{
+    Timer tx(c, SPHB_T_EXCHANGE);
+    const int W = c->world, n = c->n, B = 256, key_bits = c->P.key_levels * DIM;
+    int * cnt = c->d_mig, * cursor = c->d_mig + (W + 1), * soff_d = c->d_mig + (2 * W + 1), * mat = c->d_mig + (3 * W + 1);
+    CK(cudaMemsetAsync(c->d_mig, 0, sizeof(int) * (2 * W + 1), c->stream));
+    if (n > 0) { k_mig_mark<<<cdiv(n, B), B, 0, c->stream>>>(c->keys, n, c->d_split, W, c->rank, key_bits, cnt, c->mig_idx, c->mig_dest); LAUNCH_CHECK(); }
+    CKN(g_nccl.AllGather(cnt, mat, W, ncclInt32, c->comm, c->stream));
+    std::vector<int> hm((size_t)W * W);
+    CK(cudaMemcpyAsync(hm.data(), mat, sizeof(int) * W * W, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<int> soff(W + 1, 0), roff(W + 1, 0);
+    long long moved_all = 0;
+    for (int d = 0; d < W; ++d) { soff[d + 1] = soff[d] + hm[(size_t)c->rank * W + d]; roff[d + 1] = roff[d] + hm[(size_t)d * W + c->rank]; }
+    for (int v : hm) moved_all += v;
+    const int n_leave = soff[W], n_recv = roff[W];
+    // every rank's new count (all ranks hold the same matrix)
+    for (int r = 0; r < W; ++r) {
+        int out = 0, in = 0;
+        for (int d = 0; d < W; ++d) { out += hm[(size_t)r * W + d]; in += hm[(size_t)d * W + r]; }
+        c->n_all[r] += in - out;
+    }
+    *n_sort = n + std::max(0, n_recv - n_leave);          // arrivals first fill the leavers' slots
+    *n_new = n - n_leave + n_recv;
+    if (*n_sort > c->cap) { c->err = "domain decomposition: arrivals exceed the state capacity of this rank (load imbalance above 30 %)"; return 1; }
+    if (moved_all == 0) return 0;
+    c->migrated += (uint64_t)n_leave;
+    c->orig_valid = false;
+    if (n_leave > 0) {
+        CK(cudaMemcpyAsync(soff_d, soff.data(), sizeof(int) * W, cudaMemcpyHostToDevice, c->stream));
+        k_mig_pack<DIM><<<cdiv(n_leave, B), B, 0, c->stream>>>(c->cur, c->mig_idx, c->mig_dest, n_leave, soff_d, cursor, c->mig_send); LAUNCH_CHECK();
+    }
+    const size_t R = mig_rec(DIM);
+    CKN(g_nccl.GroupStart());
+    for (int r = 0; r < W; ++r) {
+        if (r == c->rank) continue;
+        const int ns = soff[r + 1] - soff[r], nr = roff[r + 1] - roff[r];
+        if (ns) CKN(g_nccl.Send(c->mig_send + (size_t)soff[r] * R, (size_t)ns * R, ncclFloat64, r, c->comm, c->stream));
+        if (nr) CKN(g_nccl.Recv(c->mig_recv + (size_t)roff[r] * R, (size_t)nr * R, ncclFloat64, r, c->comm, c->stream));
+    }
+    CKN(g_nccl.GroupEnd());
+    if (n_recv > 0) {
+        k_mig_unpack<DIM><<<cdiv(n_recv, B), B, 0, c->stream>>>(c->cur, c->mig_recv, n_recv, c->mig_idx, n_leave, n,
+                                                                c->d_root, c->P.key_levels, c->keys, c->idx);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+// pull every rank's sorted key run into keys_glob (replicated topology); pt.off must be current
+int gather_keys(sphb_ctx * c)
+{
+    Timer tx(c, SPHB_T_EXCHANGE);
+    if (nccl_barrier(c)) return 1;                      // every rank's keys are sorted
+    k_gather_keys<<<c->sm_count * 8, 256, 0, c->stream>>>(c->pt, c->lay.keys, c->keys_glob, c->n_glob); LAUNCH_CHECK();
+    return 0;
+}
+
+void set_offsets(sphb_ctx * c)
+{
+    int o = 0;
+    for (int r = 0; r < c->world; ++r) { c->off_all[r] = o; o += c->n_all[r]; }
+    c->off_all[c->world] = o;
+    c->off = c->off_all[c->rank];
+    c->n = c->n_all[c->rank];
+    for (int r = 0; r <= c->world; ++r) c->pt.off[r] = c->off_all[r];
 }
 
 // ---- tree ---------------------------------------------------------------------------------------------
 template <int DIM> int make_tree_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_TREE);
-    const int n = c->n;
-    const int B = 256;
+    const int B = 256, W = c->world;
+    const bool dist = W > 1;
     if (!c->P.periodic) {
-        k_bbox_partial<DIM><<<c->bbox_blocks, B, 0, c->stream>>>(c->cur, n, c->d_bbox_part); LAUNCH_CHECK();
-        k_bbox_final<DIM><<<1, 32, 0, c->stream>>>(c->d_bbox_part, c->bbox_blocks, c->d_root); LAUNCH_CHECK();
+        k_bbox_partial<DIM><<<c->bbox_blocks, B, 0, c->stream>>>(c->cur, c->n, c->d_bbox_part); LAUNCH_CHECK();
+        if (!dist) { k_bbox_final<DIM><<<1, 32, 0, c->stream>>>(c->d_bbox_part, c->bbox_blocks, c->d_root); LAUNCH_CHECK(); }
+        else {
+            k_bbox_neg<DIM><<<1, 32, 0, c->stream>>>(c->d_bbox_part, c->bbox_blocks, c->d_scal + 8); LAUNCH_CHECK();
+            CKN(g_nccl.AllReduce(c->d_scal + 8, c->d_scal + 8, 2 * DIM, ncclFloat64, ncclMax, c->comm, c->stream));
+            k_root_from_bbox<DIM><<<1, 32, 0, c->stream>>>(c->d_scal + 8, c->d_root); LAUNCH_CHECK();
+        }
     }
-    k_keys<DIM><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, n, c->d_root, c->P.key_levels, c->keys, c->idx); LAUNCH_CHECK();
+    if (c->n > 0) { k_keys<DIM><<<cdiv(c->n, B), B, 0, c->stream>>>(c->cur, 0, c->n, c->d_root, c->P.key_levels, c->keys, c->idx); LAUNCH_CHECK(); }
+    int n_sort = c->n, n_new = c->n;
+    if (dist) {
+        if (!c->split_valid) {
+            // first build: splitters = exact quantiles of all keys (one-time replicated sort of the gathered, unsorted keys)
+            CK(cudaMemcpyAsync(c->keys_alt, c->keys, sizeof(unsigned long long) * c->n, cudaMemcpyDeviceToDevice, c->stream));
+            if (gather_keys(c)) return 1;
+            unsigned long long * tmpk = nullptr;
+            CK(cudaMalloc(&tmpk, sizeof(unsigned long long) * ((size_t)c->n_glob + 32)));
+            size_t tb = c->cub_tmp_bytes;
+            CK(cub::DeviceRadixSort::SortKeys(c->cub_tmp, tb, c->keys_glob, tmpk, c->n_glob, 0, std::min(64, c->P.key_levels * DIM), c->stream));
+            ++c->launches;
+            k_next_splitters<<<1, 32, 0, c->stream>>>(tmpk, c->n_glob, W, c->d_split); LAUNCH_CHECK();
+            CK(cudaStreamSynchronize(c->stream));
+            cudaFree(tmpk);
+            if (nccl_barrier(c)) return 1;              // peers are done reading my unsorted keys
+            c->split_valid = true;
+        }
+        if (migrate_t<DIM>(c, &n_sort, &n_new)) return 1;
+    }
     // Partial radix sort: only the key levels the tree can use are sorted — one more than the depth of the
     // previous tree (the sort is stable and its input is the previous tree order).  If a node below the sorted
     // levels turns out to need a split, the build is redone with all levels (deeper flag).
@@ -378,21 +643,33 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         const int depth = (int)c->levels.size();
         if (!c->force_full_sort && depth > 0 && depth <= true_max_level) sort_levels = std::min(c->P.key_levels, depth + 1);
     }
-    size_t tmp = c->cub_tmp_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_alt, c->idx, c->idx_alt, n,
-                                       (c->P.key_levels - sort_levels) * DIM, std::min(64, c->P.key_levels * DIM), c->stream));
-    ++c->launches;
-    k_permute_pack<DIM><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->alt, c->rc, c->idx_alt, n, c->P.sph_type == T_GSPH ? 1 : 0);
-    LAUNCH_CHECK();
+    const int key_bits = c->P.key_levels * DIM;
+    if (n_sort > 0) {
+        size_t tmp = c->cub_tmp_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp, tmp, c->keys, c->keys_alt, c->idx, c->idx_alt, n_sort,
+                                           (c->P.key_levels - sort_levels) * DIM, std::min(64, key_bits + (dist ? 1 : 0)), c->stream));
+        ++c->launches;
+    }
+    if (dist) { set_offsets(c); }                       // n, off of every rank after the migration
+    const int n = c->n, N = c->n_glob;
+    if (n > 0) {
+        k_permute_pack<DIM><<<cdiv(n, B), B, 0, c->stream>>>(c->cur, c->alt, c->rc, c->idx_alt, n, c->P.sph_type == T_GSPH ? 1 : 0, c->off);
+        LAUNCH_CHECK();
+    }
     c->recs_dirty = false;
     std::swap(c->cur, c->alt);
-    const unsigned long long * keys = c->keys_alt;
+    make_global_view(c);
+    if (dist) {
+        if (gather_keys(c)) return 1;
+        k_next_splitters<<<1, 32, 0, c->stream>>>(c->keys_glob, N, W, c->d_split); LAUNCH_CHECK();   // lag-one re-balancing
+    }
+    const unsigned long long * keys = c->keys_glob;
 
-    if (c->node_cap == 0) { if (alloc_nodes(c, std::max(1024, n / 2 + 64), 0)) return 1; }
+    if (c->node_cap == 0) { if (alloc_nodes(c, std::max(1024, N / 2 + 64), 0)) return 1; }
     const int max_level_eff = std::min(true_max_level, sort_levels);
-    const long long node_limit = 5LL * n + 1;          // BHTree::resize: 5 N nodes + the root (src/bhtree.cpp:46)
+    const long long node_limit = 5LL * N + 1;          // BHTree::resize: 5 N nodes + the root (src/bhtree.cpp:46)
     CK(cudaMemsetAsync(c->d_lvl_bad, 0, 2 * sizeof(int), c->stream));     // [0] speculation failed, [1] deeper sort needed
-    k_root_init<<<1, 32, 0, c->stream>>>(c->tb, n, c->d_root); LAUNCH_CHECK();
+    k_root_init<<<1, 32, 0, c->stream>>>(c->tb, N, c->d_root); LAUNCH_CHECK();
     int lb = 0, le = 1;
     bool built = false;
     // ---- speculative build: the level widths of the previous tree (+25 %) size the grids, the level bounds
@@ -432,7 +709,7 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
             lb = h_lvl[nl];
             built = true;
         } else {
-            k_root_init<<<1, 32, 0, c->stream>>>(c->tb, n, c->d_root); LAUNCH_CHECK();
+            k_root_init<<<1, 32, 0, c->stream>>>(c->tb, N, c->d_root); LAUNCH_CHECK();
         }
     }
     if (!built) {
@@ -468,59 +745,96 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
     }
     }
     const int n_nodes = lb;
-    for (int l = (int)c->levels.size() - 1; l >= 0; --l) {
-        const int a = c->levels[l].first, b = c->levels[l].second;
-        k_level_up<DIM><<<cdiv(b - a, B), B, 0, c->stream>>>(c->tb, c->cur, a, b); LAUNCH_CHECK();
+    if (!dist) {
+        for (int l = (int)c->levels.size() - 1; l >= 0; --l) {
+            const int a = c->levels[l].first, b = c->levels[l].second;
+            k_level_up<DIM><<<cdiv(b - a, B), B, 0, c->stream>>>(c->tb, c->rc.posm, a, b, 0, N, 0); LAUNCH_CHECK();
+        }
+    } else {
+        // partial sums of the leaves over the own particles, summed across ranks, then the internal nodes bottom-up
+        k_level_up<DIM><<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, c->rc.posm, 0, n_nodes, c->off, c->off + n, 1); LAUNCH_CHECK();
+        {
+            Timer tx(c, SPHB_T_EXCHANGE);
+            CKN(g_nccl.AllReduce(c->tb.msum4, c->tb.msum4, (size_t)n_nodes * 4, ncclFloat64, ncclSum, c->comm, c->stream));
+        }
+        for (int l = (int)c->levels.size() - 1; l >= 0; --l) {
+            const int a = c->levels[l].first, b = c->levels[l].second;
+            k_level_up<DIM><<<cdiv(b - a, B), B, 0, c->stream>>>(c->tb, c->rc.posm, a, b, 0, N, 2); LAUNCH_CHECK();
+        }
     }
     c->td.n_nodes = n_nodes;
     k_tree_scatter<DIM><<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, c->td, n_nodes, c->d_root); LAUNCH_CHECK();
-    // particle groups (sphb_tree.cuh): flags at group starts -> ascending list of starts
+    // particle groups (sphb_tree.cuh) of the own range: flags at group starts -> ascending list of starts
+    if (dist) {
+        CK(cudaMemsetAsync(c->d_ncells, 0, 2 * sizeof(int), c->stream));
+        CK(cudaMemsetAsync(c->halo_flags, 0, (size_t)n_nodes + 8, c->stream));
+        CK(cudaMemsetAsync(c->halo_have, 0, (size_t)n_nodes + 8, c->stream));
+    }
     for (int kind = 0; kind < (c->P.use_gravity ? 2 : 1); ++kind) {
-        CK(cudaMemsetAsync(c->grp_flags, 0, (size_t)n, c->stream));
-        k_group_flags<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->world > 1 ? c->slice_groups * 32 : 0, n,
-                                                          kind == 0 ? GROUP_CELL_SPH : GROUP_CELL_GRAV);
+        CK(cudaMemsetAsync(c->grp_flags, 0, (size_t)n + 1, c->stream));
+        k_group_flags_own<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->off, c->off + n,
+                                                              kind == 0 ? GROUP_CELL_SPH : GROUP_CELL_GRAV,
+                                                              dist ? (kind == 0 ? c->cells_s : c->cells_g) : nullptr, dist ? c->d_ncells + kind : nullptr);
         LAUNCH_CHECK();
-        size_t tb = c->cub_tmp_bytes;
-        CK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, thrust::counting_iterator<int>(0), c->grp_flags,
-                                      kind == 0 ? c->grp_start : c->grp_start_g, kind == 0 ? c->d_ngroups : c->d_ngroups_g, n, c->stream));
-        ++c->launches;
+        if (n > 0) {
+            size_t tb = c->cub_tmp_bytes;
+            CK(cub::DeviceSelect::Flagged(c->cub_tmp, tb, thrust::counting_iterator<int>(c->off), c->grp_flags,
+                                          kind == 0 ? c->grp_start : c->grp_start_g, kind == 0 ? c->d_ngroups : c->d_ngroups_g, n, c->stream));
+            ++c->launches;
+        } else CK(cudaMemsetAsync(kind == 0 ? c->d_ngroups : c->d_ngroups_g, 0, sizeof(int), c->stream));
     }
     c->tree_valid = true;
+    c->ksize_valid = false; c->hsoft_valid = false;
     c->last_counters.tree_nodes = (uint64_t)n_nodes;
     return 0;
 }
 
+// BHTree::set_kernel: leaf maxima over the own particles -> parents; multi-GPU: max across ranks; -> walk records
 int set_kernel(sphb_ctx * c)
 {
-    k_clear_kernel<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td); LAUNCH_CHECK();
-    k_set_kernel<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td, c->cur.sml); LAUNCH_CHECK();
+    const int nn = c->td.n_nodes;
+    k_clear_kernel<<<cdiv(nn, 256), 256, 0, c->stream>>>(c->td); LAUNCH_CHECK();
+    k_set_kernel<<<cdiv(nn, 256), 256, 0, c->stream>>>(c->td, c->gv.sml, c->off, c->off + c->n); LAUNCH_CHECK();
+    if (c->world > 1) {
+        Timer tx(c, SPHB_T_EXCHANGE);
+        CKN(g_nccl.AllReduce(c->td.ksize, c->td.ksize, (size_t)nn, ncclFloat64, ncclMax, c->comm, c->stream));
+    }
+    k_apply_ksize<<<cdiv(nn, 256), 256, 0, c->stream>>>(c->td); LAUNCH_CHECK();
+    c->ksize_valid = true;
     return 0;
 }
 
-// ---- multi-GPU exchange: every rank owns slice_groups*32 consecutive particles of the sorted order
-int gather_d(sphb_ctx * c, double * a)
+// ---- multi-GPU halo: mark the remote leaves the own group cells can reach, then pull their records from the owners ------
+// phase 0: gather search of initial_smoothing (radius h_guess), 1: gather search of PreInteraction (h_guess * kernel_ratio),
+// 2: symmetric search of FluidForce + leaves the gravity walk may open.
+template <int DIM> int halo_t(sphb_ctx * c, int phase)
 {
-    const size_t cnt = (size_t)c->slice_groups * 32;
-    CKN(g_nccl.AllGather(a + cnt * c->rank, a, cnt, ncclFloat64, c->comm, c->stream));
+    if (c->world == 1) return 0;
+    Timer tx(c, SPHB_T_EXCHANGE);
+    const int grid = c->sm_count * 4;
+    if (phase < 2) {
+        k_mark_halo<DIM><<<grid, 128, 0, c->stream>>>(c->td, c->P, c->cells_s, c->d_ncells + 0, 0, 1, phase == 0 ? 1.0 : c->P.kernel_ratio,
+                                                       c->gv.mass, c->gv.dens, c->off, c->off + c->n, c->halo_flags, c->d_err);
+        LAUNCH_CHECK();
+    } else {
+        k_mark_halo<DIM><<<grid, 128, 0, c->stream>>>(c->td, c->P, c->cells_s, c->d_ncells + 0, 1, 1, 1.0,
+                                                       c->gv.mass, c->gv.dens, c->off, c->off + c->n, c->halo_flags, c->d_err);
+        LAUNCH_CHECK();
+        if (c->P.use_gravity) {
+            k_mark_halo<DIM><<<grid, 128, 0, c->stream>>>(c->td, c->P, c->cells_g, c->d_ncells + 1, 1, 2, 1.0,
+                                                           c->gv.mass, c->gv.dens, c->off, c->off + c->n, c->halo_flags, c->d_err);
+            LAUNCH_CHECK();
+        }
+    }
+    if (nccl_barrier(c)) return 1;                      // the owners' records of this phase are written
+    const int need_sph = phase < 2 ? (PULL_POSM | PULL_VELC | PULL_THERMO_A) : (PULL_POSM | PULL_VELC | PULL_THERMO_B);
+    const int need_grav = phase < 2 ? 0 : (PULL_POSM | PULL_HSOFT);
+    k_pull_halo<<<cdiv(c->td.n_nodes, 128), 128, 0, c->stream>>>(c->td, c->pt, c->lay, c->slab, c->halo_flags, c->halo_have, need_sph, need_grav, c->d_err + 3);
+    LAUNCH_CHECK();
+    if (phase == 2) { if (nccl_barrier(c)) return 1; }  // all pulls of the step are done: the owners may rewrite their records
     return 0;
 }
-int gather_i(sphb_ctx * c, int * a)
-{
-    const size_t cnt = (size_t)c->slice_groups * 32;
-    CKN(g_nccl.AllGather(a + cnt * c->rank, a, cnt, ncclInt32, c->comm, c->stream));
-    return 0;
-}
-
-// ---- stages --------------------------------------------------------------------------------------------
-// A rank computes groups [g0, g0 + ng) of the sorted order; kernels take a particle-offset view.
-struct Slice { int first_particle, n_local; };
-Slice my_slice(sphb_ctx * c)
-{
-    if (c->world == 1) return {0, c->n};
-    const long long f = (long long)c->rank * c->slice_groups * 32;
-    const long long l = std::min<long long>(c->n, f + (long long)c->slice_groups * 32);
-    return {(int)std::min<long long>(f, c->n), (int)std::max<long long>(0, l - f)};
-}
+int halo(sphb_ctx * c, int phase) { return c->dim == 1 ? halo_t<1>(c, phase) : c->dim == 2 ? halo_t<2>(c, phase) : halo_t<3>(c, phase); }
 
 } // namespace
 
@@ -529,40 +843,28 @@ namespace {
 template <int DIM, int KT, int SPH> int pre_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_PRE);
-    const Slice s = my_slice(c);
     GroupTable gt;
     if (c->first_pre) {
-        // initial_smoothing needs every particle's density before the main pass: all ranks do all
-        // particles (first call only)
-        if (ensure_recs(c) || group_table(c, 0, c->n, gt)) return 1;
-        k_initial_smoothing<DIM, KT><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt, c->d_err); LAUNCH_CHECK();
+        // initial_smoothing (src/pre_interaction.cpp:171-215), first call only
+        if (ensure_recs(c) || halo(c, 0) || group_table(c, gt)) return 1;
+        k_initial_smoothing<DIM, KT><<<c->pre_grid, 128, 0, c->stream>>>(c->gv, c->rc, c->td, c->P, gt, c->d_err); LAUNCH_CHECK();
         c->first_pre = false;
         c->recs_dirty = true;             // dens changed
     }
-    if (ensure_recs(c)) return 1;
+    if (ensure_recs(c) || halo(c, 1)) return 1;
     k_set_scalars<<<1, 1, 0, c->stream>>>(c->d_scal, 0.0, DBL_MAX, 2); LAUNCH_CHECK();
-    if (s.n_local > 0) {
-        if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
-        k_pre_interaction<DIM, KT, SPH><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt,
-            c->scratch_r, c->scratch_m, c->scratch_j, c->d_scal + 0, c->d_scal + 1, c->d_err, c->counters_on ? c->d_cnt : nullptr);
-        LAUNCH_CHECK();
-    }
+    if (group_table(c, gt)) return 1;
+    k_pre_interaction<DIM, KT, SPH><<<c->pre_grid, 128, 0, c->stream>>>(c->gv, c->rc, c->td, c->P, gt,
+        c->scratch_r, c->scratch_m, c->scratch_j, c->d_scal + 0, c->d_scal + 1, c->d_err, c->counters_on ? c->d_cnt : nullptr);
+    LAUNCH_CHECK();
+    if (c->P.use_gravity && c->n > 0) { k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, c->rc.hsoft + c->off, c->n); LAUNCH_CHECK(); }
+    c->hsoft_valid = true;
     if (c->world > 1) {
         Timer tx(c, SPHB_T_EXCHANGE);
-        PSoA & p = c->cur;
-        CKN(g_nccl.GroupStart());
-        double * arr[] = {p.sml, p.dens, p.pres, p.gradh, p.balsara, p.alpha};
-        for (double * a : arr) if (gather_d(c, a)) return 1;
-        if (gather_i(c, p.neighbor)) return 1;
-        if (SPH == T_GSPH) {
-            for (int k = 0; k < DIM; ++k) { if (gather_d(c, p.grad_d[k]) || gather_d(c, p.grad_p[k])) return 1; }
-            for (int v = 0; v < DIM; ++v) for (int k = 0; k < DIM; ++k) if (gather_d(c, p.grad_v[v][k])) return 1;
-        }
         CKN(g_nccl.AllReduce(c->d_scal + 1, c->d_scal + 1, 1, ncclFloat64, ncclMin, c->comm, c->stream));
-        CKN(g_nccl.GroupEnd());
-        if (pack_recs(c, 4)) return 1;    // the other ranks' h, dens, pres, gradh, alpha, balsara
     }
-    return set_kernel(c);
+    if (set_kernel(c)) return 1;
+    return halo(c, 2);
 }
 
 template <int DIM> int pre_d(sphb_ctx * c)
@@ -580,18 +882,31 @@ template <int DIM> int pre_d(sphb_ctx * c)
     c->err = "unsupported kernel / SPH type"; return 1;
 }
 
+// stages called on their own (module mode) after an upload: records and kernel sizes may be stale
+int refresh_for_forces(sphb_ctx * c)
+{
+    if (c->recs_dirty || !c->hsoft_valid) {
+        if (ensure_recs(c)) return 1;
+        if (c->P.use_gravity && c->n > 0) { k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, c->rc.hsoft + c->off, c->n); LAUNCH_CHECK(); }
+        c->hsoft_valid = true;
+        c->ksize_valid = false;
+    }
+    if (!c->ksize_valid) {
+        if (set_kernel(c)) return 1;
+        if (halo(c, 2)) return 1;
+    }
+    return 0;
+}
+
 template <int DIM, int KT, int SPH> int force_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_FLUID);
-    const Slice s = my_slice(c);
-    if (ensure_recs(c)) return 1;
-    if (s.n_local > 0) {
-        GroupTable gt;
-        if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt)) return 1;
-        k_fluid_force<DIM, KT, SPH><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt,
-            c->scratch_j, c->d_scal + 0, c->d_err, c->counters_on ? c->d_cnt : nullptr);
-        LAUNCH_CHECK();
-    }
+    if (refresh_for_forces(c)) return 1;
+    GroupTable gt;
+    if (group_table(c, gt)) return 1;
+    k_fluid_force<DIM, KT, SPH><<<c->pre_grid, 128, 0, c->stream>>>(c->gv, c->rc, c->td, c->P, gt,
+        c->scratch_j, c->d_scal + 0, c->d_err, c->counters_on ? c->d_cnt : nullptr);
+    LAUNCH_CHECK();
     return 0;
 }
 template <int DIM> int force_d(sphb_ctx * c)
@@ -612,7 +927,6 @@ template <int DIM> int force_d(sphb_ctx * c)
 template <int DIM> int gravity_t(sphb_ctx * c, bool direct, int k_targets = 0)
 {
     Timer tm(c, SPHB_T_GRAVITY);
-    const Slice s = my_slice(c);
     if (direct) {
         if (c->world > 1) { c->err = "sphb_gravity_direct is single-GPU only"; return 1; }
         if (k_targets > 0 && k_targets < c->n) {
@@ -626,50 +940,31 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct, int k_targets = 0)
         k_gravity_direct<DIM><<<cdiv(c->n, 128), 128, 0, c->stream>>>(c->cur, c->P, c->n, nullptr, c->n); LAUNCH_CHECK();
         return 0;
     }
-    if (s.n_local > 0) {
-        if (ensure_recs(c)) return 1;
-        k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, c->rc.hsoft, c->n); LAUNCH_CHECK();
-        k_grav_leaf_h<<<cdiv(c->td.n_nodes, 256), 256, 0, c->stream>>>(c->td, c->cur.sml); LAUNCH_CHECK();
-        GroupTable gt;
-        if (group_table(c, s.first_particle, s.first_particle + s.n_local, gt, true)) return 1;
-        const int smem = (int)(4 * sizeof(GravSmem));
+    if (refresh_for_forces(c)) return 1;
+    GroupTable gt;
+    if (group_table(c, gt, true)) return 1;
+    const int smem = (int)(4 * sizeof(GravSmem));
 #define SPHB_GRAV(PER, CNT) do { \
-            bool & attr_set = c->grav_attr_set[PER ? 1 : 0][CNT ? 1 : 0];      /* per context: the attribute is per device */ \
-            if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity<DIM, PER, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; } \
-            k_gravity<DIM, PER, CNT><<<c->grav_grid, 128, smem, c->stream>>>(c->cur, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, \
-                c->grav_lq, c->grav_near, c->d_cnt, c->d_err); } while (0)
-        if (c->P.periodic) { if (c->counters_on) SPHB_GRAV(true, true); else SPHB_GRAV(true, false); }
-        else               { if (c->counters_on) SPHB_GRAV(false, true); else SPHB_GRAV(false, false); }
+        bool & attr_set = c->grav_attr_set[PER ? 1 : 0][CNT ? 1 : 0];      /* per context: the attribute is per device */ \
+        if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity<DIM, PER, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; } \
+        k_gravity<DIM, PER, CNT><<<c->grav_grid, 128, smem, c->stream>>>(c->gv, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, \
+            c->grav_lq, c->grav_near, c->d_cnt, c->d_err); } while (0)
+    if (c->P.periodic) { if (c->counters_on) SPHB_GRAV(true, true); else SPHB_GRAV(true, false); }
+    else               { if (c->counters_on) SPHB_GRAV(false, true); else SPHB_GRAV(false, false); }
 #undef SPHB_GRAV
-        LAUNCH_CHECK();
-    }
-    return 0;
-}
-
-// after fluid force (+ gravity): make acc / dene / phi whole again on every rank
-template <int DIM> int exchange_forces(sphb_ctx * c)
-{
-    if (c->world == 1) return 0;
-    Timer tx(c, SPHB_T_EXCHANGE);
-    PSoA & p = c->cur;
-    CKN(g_nccl.GroupStart());
-    for (int d = 0; d < DIM; ++d) if (gather_d(c, p.acc[d])) return 1;
-    if (gather_d(c, p.dene)) return 1;
-    if (c->P.use_gravity && gather_d(c, p.phi)) return 1;
-    CKN(g_nccl.GroupEnd());
+    LAUNCH_CHECK();
     return 0;
 }
 
 template <int DIM> int timestep_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_TIMESTEP);
-    // the force minimum is taken over the rank's slice and all-reduced (min)
-    const Slice s = my_slice(c);
+    // the force minimum is taken over the own particles and all-reduced (min)
     const double big = DBL_MAX;
     CK(cudaMemcpyAsync(c->d_scal + 2, &big, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (s.n_local > 0) {
-        const int grid = std::min(cdiv(s.n_local, 256), 4 * c->sm_count);
-        k_timestep_partial<DIM><<<grid, 256, 0, c->stream>>>(c->cur, s.first_particle, s.first_particle + s.n_local, c->P.cfl_force, c->d_scal + 2);
+    if (c->n > 0) {
+        const int grid = std::min(cdiv(c->n, 256), 4 * c->sm_count);
+        k_timestep_partial<DIM><<<grid, 256, 0, c->stream>>>(c->cur, 0, c->n, c->P.cfl_force, c->d_scal + 2);
         LAUNCH_CHECK();
     }
     if (c->world > 1) CKN(g_nccl.AllReduce(c->d_scal + 2, c->d_scal + 2, 1, ncclFloat64, ncclMin, c->comm, c->stream));
@@ -680,7 +975,7 @@ template <int DIM> int timestep_t(sphb_ctx * c)
 template <int DIM> int predict_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_PREDICT);
-    k_predict<DIM><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n, c->d_scal + 0); LAUNCH_CHECK();
+    if (c->n > 0) { k_predict<DIM><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n, c->d_scal + 0); LAUNCH_CHECK(); }
     c->tree_valid = false;
     c->recs_dirty = true;
     return 0;
@@ -688,7 +983,7 @@ template <int DIM> int predict_t(sphb_ctx * c)
 template <int DIM> int correct_t(sphb_ctx * c)
 {
     Timer tm(c, SPHB_T_CORRECT);
-    k_correct<DIM><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n, c->d_scal + 0); LAUNCH_CHECK();
+    if (c->n > 0) { k_correct<DIM><<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n, c->d_scal + 0); LAUNCH_CHECK(); }
     c->recs_dirty = true;
     return 0;
 }
@@ -699,20 +994,23 @@ int make_tree(sphb_ctx * c) { return DIM_SWITCH(c, make_tree_t<1>(c), make_tree_
 int pre(sphb_ctx * c) { return DIM_SWITCH(c, pre_d<1>(c), pre_d<2>(c), pre_d<3>(c)); }
 int force(sphb_ctx * c) { return DIM_SWITCH(c, force_d<1>(c), force_d<2>(c), force_d<3>(c)); }
 int gravity(sphb_ctx * c, bool direct, int k = 0) { return DIM_SWITCH(c, gravity_t<1>(c, direct, k), gravity_t<2>(c, direct, k), gravity_t<3>(c, direct, k)); }
-int exchange(sphb_ctx * c) { return DIM_SWITCH(c, exchange_forces<1>(c), exchange_forces<2>(c), exchange_forces<3>(c)); }
 int timestep(sphb_ctx * c) { return DIM_SWITCH(c, timestep_t<1>(c), timestep_t<2>(c), timestep_t<3>(c)); }
 int predict(sphb_ctx * c) { return DIM_SWITCH(c, predict_t<1>(c), predict_t<2>(c), predict_t<3>(c)); }
 int correct(sphb_ctx * c) { return DIM_SWITCH(c, correct_t<1>(c), correct_t<2>(c), correct_t<3>(c)); }
 
-// copy dt, h_per_v_sig and the error counters to the host; turn device-side errors into a status
-int sync_scalars(sphb_ctx * c)
+// copy dt, h_per_v_sig and the error counters to the host; turn device-side errors into a status.
+// collective = every rank is in this call (stage entry points): the error words are all-reduced first, so that all
+// ranks leave with the same status instead of one returning early and the others waiting in the next collective.
+int sync_scalars(sphb_ctx * c, bool collective = false)
 {
-    double s[2]; unsigned long long e[3];
+    double s[2]; unsigned long long e[4];
+    if (collective && c->world > 1) CKN(g_nccl.AllReduce(c->d_err + 1, c->d_err + 1, 2, ncclUint64, ncclMax, c->comm, c->stream));
     CK(cudaMemcpyAsync(s, c->d_scal, sizeof(s), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(e, c->d_err, sizeof(e), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     c->dt = s[0]; c->hpvs = s[1];
     c->nonconverged_total = e[0];
+    c->halo_pulled = e[3];
     if (e[1]) {
         c->err = "neighbor list overflow: a particle has more than neighborNumber*20 candidates (include/defines.hpp:29)";
         CK(cudaMemsetAsync(c->d_err + 1, 0, sizeof(unsigned long long), c->stream));
@@ -723,15 +1021,13 @@ int sync_scalars(sphb_ctx * c)
         CK(cudaMemsetAsync(c->d_err + 2, 0, sizeof(unsigned long long), c->stream));
         return 1;
     }
-    if (c->timers_on) {
-        for (int k = 0; k < SPHB_T_COUNT; ++k) if (c->ev_used[k]) cudaEventElapsedTime(&c->ms[k], c->ev[2 * k], c->ev[2 * k + 1]);
-    }
+    if (c->timers_on) read_timers(c);
     return 0;
 }
 
 int require_tree(sphb_ctx * c)
 {
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
     if (!c->tree_valid) { c->err = "tree is not made for the current positions (call sphb_make_tree)"; return 1; }
     return 0;
 }
@@ -774,24 +1070,31 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
     P.G = hp->G; P.theta = hp->theta; P.theta2 = hp->theta * hp->theta;
     P.gsph2 = hp->gsph_2nd_order;
     P.kernel_ratio = hp->iterative_sml ? 1.2 : 1.0;
-    P.key_levels = std::max(1, std::min(hp->max_tree_level, 63 / dim));
+    // the octree key holds maxTreeLevel * DIM bits (+ one spare bit for the multi-GPU migration): 20 (the default) fits
+    // every DIM; deeper trees than the key can describe are refused instead of silently truncated
+    if (hp->max_tree_level < 1 || (long long)hp->max_tree_level * dim > 63) {
+        g_create_error = "maxTreeLevel * DIM must be in [1, 63] (the 64-bit octree key cannot describe a deeper tree)";
+        delete c; return 1;
+    }
+    P.key_levels = hp->max_tree_level;
     P.list_cap = hp->neighbor_number * 20;
-    cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     c->stream = c->own_stream;
-    void * q = nullptr;
-    cudaMalloc(&q, 4 * sizeof(double)); c->d_root = (double *)q;
-    cudaMalloc(&q, 8 * sizeof(double)); c->d_scal = (double *)q;
-    cudaMalloc(&q, 4 * sizeof(unsigned long long)); c->d_err = (unsigned long long *)q;
-    cudaMalloc(&q, sizeof(Counters)); c->d_cnt = (Counters *)q;
-    cudaMalloc(&q, (SPHB_MAX_LEVELS + 4) * sizeof(int)); c->d_lvl = (int *)q;
-    cudaMalloc(&q, 2 * sizeof(int)); c->d_lvl_bad = (int *)q;
-    cudaMalloc(&q, sizeof(int)); c->d_ngroups = (int *)q;
-    cudaMalloc(&q, sizeof(int)); c->d_ngroups_g = (int *)q;
-    cudaMalloc(&q, 2 * sizeof(int)); c->d_grp_ctl = (int *)q;
-    cudaMemset(c->d_scal, 0, 8 * sizeof(double));
-    cudaMemset(c->d_err, 0, 4 * sizeof(unsigned long long));
-    cudaMemset(c->d_cnt, 0, sizeof(Counters));
-    if (P.periodic) {
+    auto alloc = [&](auto ** p, size_t bytes) { void * q = nullptr; if (ok && cudaMalloc(&q, bytes) != cudaSuccess) ok = false; *p = static_cast<std::remove_reference_t<decltype(**p)> *>(q); };
+    alloc(&c->d_root, 4 * sizeof(double));
+    alloc(&c->d_scal, 16 * sizeof(double));
+    alloc(&c->d_err, 4 * sizeof(unsigned long long));
+    alloc(&c->d_cnt, sizeof(Counters));
+    alloc(&c->d_lvl, (SPHB_MAX_LEVELS + 4) * sizeof(int));
+    alloc(&c->d_lvl_bad, 2 * sizeof(int));
+    alloc(&c->d_ngroups, sizeof(int));
+    alloc(&c->d_ngroups_g, sizeof(int));
+    alloc(&c->d_grp_ctl, 2 * sizeof(int));
+    if (ok) {
+        ok = cudaMemset(c->d_scal, 0, 16 * sizeof(double)) == cudaSuccess && cudaMemset(c->d_err, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+             cudaMemset(c->d_cnt, 0, sizeof(Counters)) == cudaSuccess;
+    }
+    if (ok && P.periodic) {
         // BHTree::initialize, src/bhtree.cpp:19-31
         double root[4] = {0, 0, 0, 0};
         double l = 0.0;
@@ -800,11 +1103,16 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
             if (l < P.range[d]) l = P.range[d];
         }
         root[3] = l;
-        cudaMemcpy(c->d_root, root, sizeof(root), cudaMemcpyHostToDevice);
+        ok = cudaMemcpy(c->d_root, root, sizeof(root), cudaMemcpyHostToDevice) == cudaSuccess;
     }
-    for (int k = 0; k < 2 * SPHB_T_COUNT; ++k) cudaEventCreate(&c->ev[k]);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete c; return 1; }
+    for (int k = 0; ok && k < SPHB_T_COUNT; ++k)
+        for (int sgm = 0; ok && sgm < SPHB_TSEG; ++sgm)
+            ok = cudaEventCreate(&c->ev[k][sgm][0]) == cudaSuccess && cudaEventCreate(&c->ev[k][sgm][1]) == cudaSuccess;
+    if (!ok) {
+        g_create_error = std::string("sphb_create: ") + cudaGetErrorString(cudaGetLastError());
+        sphb_destroy(c);
+        return 1;
+    }
     *out = c;
     return 0;
 }
@@ -815,11 +1123,12 @@ void sphb_destroy(sphb_ctx * c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->comm && c->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    close_peers(c);
     free_bag(c->allocs); free_bag(c->node_allocs);
     cudaFree(c->d_root); cudaFree(c->d_scal); cudaFree(c->d_err); cudaFree(c->d_cnt); cudaFree(c->d_lvl); cudaFree(c->d_lvl_bad); cudaFree(c->d_ngroups); cudaFree(c->d_ngroups_g); cudaFree(c->d_grp_ctl);
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    for (auto & ev : c->ev) if (ev) cudaEventDestroy(ev);
-    cudaStreamDestroy(c->own_stream);
+    for (auto & k : c->ev) for (auto & sgm : k) for (auto & ev : sgm) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -827,13 +1136,17 @@ const char * sphb_last_error(const sphb_ctx * c) { return c ? c->err.c_str() : g
 
 int sphb_set_stream(sphb_ctx * c, void * s)
 {
-    cudaStreamSynchronize(c->stream);
-    c->stream = (cudaStream_t)s;
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;          // NULL: back to the context's own stream
     return 0;
 }
 int sphb_synchronize(sphb_ctx * c) { CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return 0; }
 int sphb_dim(const sphb_ctx * c) { return c->dim; }
 int sphb_particle_num(const sphb_ctx * c) { return c->n; }
+long long sphb_global_particle_num(const sphb_ctx * c) { return c->n_glob; }
+long long sphb_first_global_index(const sphb_ctx * c) { return c->off; }
 
 int sphb_nccl_unique_id(void * out128)
 {
@@ -848,7 +1161,7 @@ int sphb_nccl_unique_id(void * out128)
 int sphb_set_distributed(sphb_ctx * c, int rank, int world, void * nccl_comm)
 {
     if (world < 1 || rank < 0 || rank >= world) { c->err = "bad rank / world"; return 1; }
-    if (c->n) { c->err = "sphb_set_distributed must precede the first upload"; return 1; }
+    if (c->n_glob) { c->err = "sphb_set_distributed must precede the first upload"; return 1; }
     if (world > 1) {
         if (!g_nccl.load(c->err)) return 1;
         if (!nccl_comm) { c->err = "nccl communicator required"; return 1; }
@@ -861,7 +1174,7 @@ int sphb_set_distributed(sphb_ctx * c, int rank, int world, void * nccl_comm)
 int sphb_set_distributed_id(sphb_ctx * c, int rank, int world, const void * unique_id128)
 {
     if (world < 1 || rank < 0 || rank >= world) { c->err = "bad rank / world"; return 1; }
-    if (c->n) { c->err = "sphb_set_distributed_id must precede the first upload"; return 1; }
+    if (c->n_glob) { c->err = "sphb_set_distributed_id must precede the first upload"; return 1; }
     if (world > 1) {
         if (!g_nccl.load(c->err)) return 1;
         CK(cudaSetDevice(c->device));
@@ -876,25 +1189,45 @@ int sphb_set_distributed_id(sphb_ctx * c, int rank, int world, const void * uniq
 }
 
 // ---- state transfer -----------------------------------------------------------------------------------
+// Device-visible address of a caller buffer when it is pinned / registered host memory (sphb_host_alloc,
+// cudaHostRegister): the pack / unpack kernels then read and write the caller's SPHParticle records in place over
+// PCIe, touching only the members in the field mask.  nullptr for pageable memory (staged copies instead).
+static void * mapped_host(const void * p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type == cudaMemoryTypeHost && a.devicePointer) return a.devicePointer;
+    return nullptr;
+}
+
 int sphb_upload_aos(sphb_ctx * c, const void * particles, int n, size_t stride, uint32_t mask)
 {
     CK(cudaSetDevice(c->device));
     const size_t rec = rec_size(c->dim);
     if (!particles || n <= 0 || stride < rec) { c->err = "bad upload arguments"; return 1; }
-    const bool first = (n != c->n);
+    const bool first = (c->n_glob == 0 || n != c->n);
     if (first) {
         if ((mask & SPHB_F_ALL) != SPHB_F_ALL) { c->err = "the first upload must use SPHB_F_ALL"; return 1; }
         if (alloc_particles(c, n)) return 1;
+    } else if (!c->orig_valid) {
+        c->err = "multi-GPU mode: particles migrated since the last download; download (which renumbers the rank's particles) before uploading into them";
+        return 1;
     }
-    if (stride == rec) CK(cudaMemcpyAsync(c->d_aos, particles, rec * n, cudaMemcpyHostToDevice, c->stream));
+    const bool full = (mask & SPHB_F_ALL) == SPHB_F_ALL;
+    const char * src = (const char *)c->d_aos;
+    size_t src_stride = rec;
+    void * mp = full ? nullptr : mapped_host(particles);
+    if (mp) { src = (const char *)mp; src_stride = stride; }            // masked upload straight from pinned host memory
+    else if (stride == rec) CK(cudaMemcpyAsync(c->d_aos, particles, rec * n, cudaMemcpyHostToDevice, c->stream));
     else CK(cudaMemcpy2DAsync(c->d_aos, rec, particles, stride, rec, n, cudaMemcpyHostToDevice, c->stream));
     switch (c->dim) {
-    case 1: k_unpack<1><<<cdiv(n, 256), 256, 0, c->stream>>>((const char *)c->d_aos, rec, c->cur, n, mask, first); break;
-    case 2: k_unpack<2><<<cdiv(n, 256), 256, 0, c->stream>>>((const char *)c->d_aos, rec, c->cur, n, mask, first); break;
-    default: k_unpack<3><<<cdiv(n, 256), 256, 0, c->stream>>>((const char *)c->d_aos, rec, c->cur, n, mask, first); break;
+    case 1: k_unpack<1><<<cdiv(n, 256), 256, 0, c->stream>>>(src, src_stride, c->cur, n, mask, first); break;
+    case 2: k_unpack<2><<<cdiv(n, 256), 256, 0, c->stream>>>(src, src_stride, c->cur, n, mask, first); break;
+    default: k_unpack<3><<<cdiv(n, 256), 256, 0, c->stream>>>(src, src_stride, c->cur, n, mask, first); break;
     }
     LAUNCH_CHECK();
     c->recs_dirty = true;
+    if (mask & SPHB_F_SML) { c->ksize_valid = false; c->hsoft_valid = false; }
     if (mask & (SPHB_F_POS | SPHB_F_MASS)) c->tree_valid = false;
     CK(cudaStreamSynchronize(c->stream));        // the caller may reuse its buffer
     return 0;
@@ -904,35 +1237,63 @@ int sphb_download_aos(sphb_ctx * c, void * particles, int n, size_t stride, uint
 {
     CK(cudaSetDevice(c->device));
     const size_t rec = rec_size(c->dim);
-    if (!particles || n != c->n || stride < rec) { c->err = "bad download arguments"; return 1; }
+    if (!particles || n != c->n || stride < rec) { c->err = "bad download arguments (n must be sphb_particle_num())"; return 1; }
+    if (!c->orig_valid) {
+        // multi-GPU: the rank's set changed by migration; the caller's record k is now the k-th own particle in tree order
+        k_renumber_orig<<<cdiv(n, 256), 256, 0, c->stream>>>(c->cur.orig, n); LAUNCH_CHECK();
+        c->orig_valid = true;
+    }
+    const bool full = (mask & SPHB_F_ALL) == SPHB_F_ALL;
+    void * mp = full ? nullptr : mapped_host(particles);
+    char * dst = mp ? (char *)mp : (char *)c->d_aos;
+    const size_t dst_stride = mp ? stride : rec;
+    // staged path of a masked download: every member is packed, the host picks the masked ones out of the staging copy
+    const uint32_t pack_mask = mp ? mask : (uint32_t)SPHB_F_ALL;
     switch (c->dim) {
-    case 1: k_pack<1><<<cdiv(n, 256), 256, 0, c->stream>>>((char *)c->d_aos, rec, c->cur, n); break;
-    case 2: k_pack<2><<<cdiv(n, 256), 256, 0, c->stream>>>((char *)c->d_aos, rec, c->cur, n); break;
-    default: k_pack<3><<<cdiv(n, 256), 256, 0, c->stream>>>((char *)c->d_aos, rec, c->cur, n); break;
+    case 1: k_pack<1><<<cdiv(n, 256), 256, 0, c->stream>>>(dst, dst_stride, c->cur, n, pack_mask); break;
+    case 2: k_pack<2><<<cdiv(n, 256), 256, 0, c->stream>>>(dst, dst_stride, c->cur, n, pack_mask); break;
+    default: k_pack<3><<<cdiv(n, 256), 256, 0, c->stream>>>(dst, dst_stride, c->cur, n, pack_mask); break;
     }
     LAUNCH_CHECK();
-    if ((mask & SPHB_F_ALL) == SPHB_F_ALL) {
+    if (mp) { CK(cudaStreamSynchronize(c->stream)); return 0; }          // written in place over PCIe
+    if (full) {
         if (stride == rec) CK(cudaMemcpyAsync(particles, c->d_aos, rec * n, cudaMemcpyDeviceToHost, c->stream));
         else CK(cudaMemcpy2DAsync(particles, stride, c->d_aos, rec, rec, n, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return 0;
     }
+    // pageable destination, partial mask: staged copy of the records, then the masked members are copied by host threads
     if (c->h_stage_bytes < rec * n) {
         if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr; c->h_stage_bytes = 0;
         CK(cudaMallocHost(&c->h_stage, rec * n));
         c->h_stage_bytes = rec * n;
     }
     CK(cudaMemcpyAsync(c->h_stage, c->d_aos, rec * n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     const int D = c->dim;
+    // contiguous byte runs of the selected members within a record
+    std::vector<std::pair<size_t, size_t>> runs;
+    auto add = [&](size_t o, size_t len) { if (!runs.empty() && runs.back().first + runs.back().second == o) runs.back().second += len; else runs.push_back({o, len}); };
     const uint32_t vec_bits[4] = {SPHB_F_POS, SPHB_F_VEL, SPHB_F_VEL_P, SPHB_F_ACC};
-    for (int i = 0; i < n; ++i) {
-        const char * src = (const char *)c->h_stage + (size_t)i * rec;
-        char * dst = (char *)particles + (size_t)i * stride;
-        for (int v = 0; v < 4; ++v) if (mask & vec_bits[v]) std::memcpy(dst + (size_t)v * D * 8, src + (size_t)v * D * 8, (size_t)D * 8);
-        for (int k = 0; k < 12; ++k) if (mask & (SPHB_F_MASS << k)) std::memcpy(dst + (size_t)(4 * D + k) * 8, src + (size_t)(4 * D + k) * 8, 8);
-        if (mask & SPHB_F_ID) std::memcpy(dst + (size_t)(4 * D + 12) * 8, src + (size_t)(4 * D + 12) * 8, 4);
-        if (mask & SPHB_F_NEIGHBOR) std::memcpy(dst + (size_t)(4 * D + 12) * 8 + 4, src + (size_t)(4 * D + 12) * 8 + 4, 4);
+    for (int v = 0; v < 4; ++v) if (mask & vec_bits[v]) add((size_t)v * D * 8, (size_t)D * 8);
+    for (int k = 0; k < 12; ++k) if (mask & (SPHB_F_MASS << k)) add((size_t)(4 * D + k) * 8, 8);
+    if (mask & SPHB_F_ID) add((size_t)(4 * D + 12) * 8, 4);
+    if (mask & SPHB_F_NEIGHBOR) add((size_t)(4 * D + 12) * 8 + 4, 4);
+    const int nth = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto work = [&](int t) {
+        const long long i0 = (long long)n * t / nth, i1 = (long long)n * (t + 1) / nth;
+        for (long long i = i0; i < i1; ++i) {
+            const char * s_ = (const char *)c->h_stage + (size_t)i * rec;
+            char * d_ = (char *)particles + (size_t)i * stride;
+            for (const auto & r : runs) std::memcpy(d_ + r.first, s_ + r.first, r.second);
+        }
+    };
+    if (nth == 1 || n < (1 << 16)) { for (int t = 0; t < nth; ++t) work(t); }
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nth; ++t) th.emplace_back(work, t);
+        for (auto & t : th) t.join();
     }
     return 0;
 }
@@ -993,11 +1354,12 @@ int sphb_set_h_per_v_sig(sphb_ctx * c, double v)
 int sphb_get_h_per_v_sig(sphb_ctx * c, double * v) { CK(cudaSetDevice(c->device)); if (sync_scalars(c)) return 1; *v = c->hpvs; return 0; }
 
 // ---- the hot path -----------------------------------------------------------------------------------------
+// In the multi-GPU mode every entry point below is COLLECTIVE: all ranks call it, in the same order.
 int sphb_init_state(sphb_ctx * c)
 {
     CK(cudaSetDevice(c->device));
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
-    k_init_state<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n); LAUNCH_CHECK();
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
+    if (c->n > 0) { k_init_state<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur, c->P, c->n); LAUNCH_CHECK(); }
     c->recs_dirty = true;
     return 0;
 }
@@ -1005,7 +1367,7 @@ int sphb_init_state(sphb_ctx * c)
 int sphb_make_tree(sphb_ctx * c)
 {
     CK(cudaSetDevice(c->device));
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
     return make_tree(c);
 }
 
@@ -1014,16 +1376,14 @@ int sphb_pre_interaction(sphb_ctx * c)
     CK(cudaSetDevice(c->device));
     if (require_tree(c)) return 1;
     if (pre(c)) return 1;
-    return sync_scalars(c);
+    return sync_scalars(c, true);
 }
 
 int sphb_fluid_force(sphb_ctx * c)
 {
     CK(cudaSetDevice(c->device));
     if (require_tree(c)) return 1;
-    if (force(c)) return 1;
-    if (!c->P.use_gravity) { if (exchange(c)) return 1; }
-    return 0;
+    return force(c);
 }
 
 int sphb_gravity_force(sphb_ctx * c)
@@ -1031,15 +1391,14 @@ int sphb_gravity_force(sphb_ctx * c)
     CK(cudaSetDevice(c->device));
     if (!c->P.use_gravity) return 0;                  // src/gravity_force.cpp:54-56
     if (require_tree(c)) return 1;
-    if (gravity(c, false)) return 1;
-    return exchange(c);
+    return gravity(c, false);
 }
 
 int sphb_gravity_direct(sphb_ctx * c)
 {
     CK(cudaSetDevice(c->device));
     if (!c->P.use_gravity) return 0;
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
     return gravity(c, true);
 }
 
@@ -1047,7 +1406,7 @@ int sphb_gravity_direct_targets(sphb_ctx * c, int k)
 {
     CK(cudaSetDevice(c->device));
     if (!c->P.use_gravity) return 0;
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
     if (k <= 0) { c->err = "bad target count"; return 1; }
     return gravity(c, true, k);
 }
@@ -1055,34 +1414,33 @@ int sphb_gravity_direct_targets(sphb_ctx * c, int k)
 int sphb_timestep(sphb_ctx * c, double * dt)
 {
     CK(cudaSetDevice(c->device));
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
     if (timestep(c)) return 1;
-    if (sync_scalars(c)) return 1;
+    if (sync_scalars(c, true)) return 1;
     if (dt) *dt = c->dt;
     return 0;
 }
 
-int sphb_predict(sphb_ctx * c) { CK(cudaSetDevice(c->device)); if (!c->n) { c->err = "no particles uploaded"; return 1; } return predict(c); }
-int sphb_correct(sphb_ctx * c) { CK(cudaSetDevice(c->device)); if (!c->n) { c->err = "no particles uploaded"; return 1; } return correct(c); }
+int sphb_predict(sphb_ctx * c) { CK(cudaSetDevice(c->device)); if (!c->n_glob) { c->err = "no particles uploaded"; return 1; } return predict(c); }
+int sphb_correct(sphb_ctx * c) { CK(cudaSetDevice(c->device)); if (!c->n_glob) { c->err = "no particles uploaded"; return 1; } return correct(c); }
 
 int sphb_initialize(sphb_ctx * c)
 {
     CK(cudaSetDevice(c->device));
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
     if (sphb_init_state(c) || make_tree(c) || pre(c) || force(c)) return 1;
     if (c->P.use_gravity) { if (gravity(c, false)) return 1; }
-    if (exchange(c)) return 1;
-    return sync_scalars(c);
+    return sync_scalars(c, true);
 }
 
 int sphb_integrate(sphb_ctx * c, double * dt)
 {
     CK(cudaSetDevice(c->device));
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
     if (timestep(c) || predict(c) || make_tree(c) || pre(c) || force(c)) return 1;
     if (c->P.use_gravity) { if (gravity(c, false)) return 1; }
-    if (exchange(c) || correct(c)) return 1;
-    if (sync_scalars(c)) return 1;
+    if (correct(c)) return 1;
+    if (sync_scalars(c, true)) return 1;
     if (dt) *dt = c->dt;
     return 0;
 }
@@ -1090,15 +1448,18 @@ int sphb_integrate(sphb_ctx * c, double * dt)
 int sphb_energy(sphb_ctx * c, double out[3])
 {
     CK(cudaSetDevice(c->device));
-    if (!c->n) { c->err = "no particles uploaded"; return 1; }
+    if (!c->n_glob) { c->err = "no particles uploaded"; return 1; }
     CK(cudaMemsetAsync(c->d_scal + 3, 0, 3 * sizeof(double), c->stream));
-    const int grid = std::min(cdiv(c->n, 256), 4 * c->sm_count);
-    switch (c->dim) {
-    case 1: k_energy<1><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
-    case 2: k_energy<2><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
-    default: k_energy<3><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
+    if (c->n > 0) {
+        const int grid = std::min(cdiv(c->n, 256), 4 * c->sm_count);
+        switch (c->dim) {
+        case 1: k_energy<1><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
+        case 2: k_energy<2><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
+        default: k_energy<3><<<grid, 256, 0, c->stream>>>(c->cur, c->n, c->d_scal + 3); break;
+        }
+        LAUNCH_CHECK();
     }
-    LAUNCH_CHECK();
+    if (c->world > 1) CKN(g_nccl.AllReduce(c->d_scal + 3, c->d_scal + 3, 3, ncclFloat64, ncclSum, c->comm, c->stream));
     CK(cudaMemcpyAsync(out, c->d_scal + 3, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -1109,6 +1470,7 @@ int sphb_neighbor_lists(sphb_ctx * c, const double * h, int symmetric, int64_t *
 {
     CK(cudaSetDevice(c->device));
     if (require_tree(c)) return 1;
+    if (c->world > 1) { c->err = "sphb_neighbor_lists is a single-GPU test hook"; return 1; }
     const int n = c->n;
     if (ensure_recs(c)) return 1;
     if (symmetric) { if (set_kernel(c)) return 1; }
@@ -1122,7 +1484,7 @@ int sphb_neighbor_lists(sphb_ctx * c, const double * h, int symmetric, int64_t *
     }
     if (dev_alloc(c, &d_counts, n, bag) || dev_alloc(c, &d_offs, n + 1, bag)) { free_bag(bag); return 1; }
     GroupTable gt;
-#define NL(D, FILL) if (group_table(c, 0, n, gt)) { free_bag(bag); return 1; } k_neighbor_lists<D><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt, d_h, symmetric, FILL, d_counts, d_offs, d_ids, cap_total, c->d_err)
+#define NL(D, FILL) if (group_table(c, gt)) { free_bag(bag); return 1; } k_neighbor_lists<D><<<c->pre_grid, 128, 0, c->stream>>>(c->cur, c->rc, c->td, c->P, gt, d_h, symmetric, FILL, d_counts, d_offs, d_ids, cap_total, c->d_err)
     switch (c->dim) { case 1: NL(1, 0); break; case 2: NL(2, 0); break; default: NL(3, 0); break; }
     LAUNCH_CHECK();
     std::vector<int> counts(n), orig(n);
@@ -1195,17 +1557,17 @@ int sphb_get_counters(sphb_ctx * c, sphb_counters * out)
     return 0;
 }
 
-int sphb_enable_timers(sphb_ctx * c, int enable) { c->timers_on = enable != 0; for (auto & u : c->ev_used) u = false; for (auto & m : c->ms) m = 0.f; return 0; }
+int sphb_enable_timers(sphb_ctx * c, int enable) { c->timers_on = enable != 0; for (auto & u : c->nseg) u = 0; for (auto & m : c->ms) m = 0.f; return 0; }
 int sphb_get_timers(sphb_ctx * c, float ms[SPHB_T_COUNT])
 {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < SPHB_T_COUNT; ++k) {
-        if (c->ev_used[k]) cudaEventElapsedTime(&c->ms[k], c->ev[2 * k], c->ev[2 * k + 1]);
-        ms[k] = c->ms[k];
-    }
+    read_timers(c);
+    for (int k = 0; k < SPHB_T_COUNT; ++k) ms[k] = c->ms[k];
     return 0;
 }
+uint64_t sphb_halo_records(const sphb_ctx * c) { return c->halo_pulled; }
+uint64_t sphb_migrated(const sphb_ctx * c) { return c->migrated; }
 
 uint64_t sphb_launch_count(const sphb_ctx * c) { return c->launches; }
 uint64_t sphb_nonconverged(const sphb_ctx * c) { return c->nonconverged_total; }

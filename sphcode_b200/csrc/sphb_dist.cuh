@@ -118,12 +118,14 @@ __global__ void k_mig_pack(PSoA s, const int * __restrict__ list_idx, const int 
     q[12] = pack_ints(s.pid[i], s.neighbor[i]);
     q[13] = pack_ints(s.orig[i], 0);
 }
+// arrival t goes into the slot of this rank's t-th leaver, the rest behind the own particles (index n_own, n_own + 1, ...)
 template <int DIM>
-__global__ void k_mig_unpack(PSoA s, const double * __restrict__ buf, int count, int at)
+__global__ void k_mig_unpack(PSoA s, const double * __restrict__ buf, int count, const int * __restrict__ list_idx, int n_leave, int n_own,
+                             const double * __restrict__ root, int key_levels, unsigned long long * __restrict__ keys, int * __restrict__ idx)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
-    const int i = at + t;
+    const int i = t < n_leave ? list_idx[t] : n_own + (t - n_leave);
     const double * r = buf + (size_t)t * mig_rec(DIM);
 #pragma unroll
     for (int a = 0; a < DIM; ++a) { s.pos[a][i] = r[a]; s.vel[a][i] = r[DIM + a]; s.vel_p[a][i] = r[2 * DIM + a]; s.acc[a][i] = r[3 * DIM + a]; }
@@ -132,16 +134,12 @@ __global__ void k_mig_unpack(PSoA s, const double * __restrict__ buf, int count,
     s.sml[i] = q[6]; s.sound[i] = q[7]; s.balsara[i] = q[8]; s.alpha[i] = q[9]; s.gradh[i] = q[10]; s.phi[i] = q[11];
     s.pid[i] = __double2loint(q[12]); s.neighbor[i] = __double2hiint(q[12]);
     s.orig[i] = __double2loint(q[13]);
+    keys[i] = key_of<DIM>(s, i, root, key_levels);
+    idx[i] = i;
 }
 
-// evenly spaced sample of a sorted key array (splitter selection of the first build)
-__global__ void k_sample_keys(const unsigned long long * __restrict__ sorted, int n, int ns, unsigned long long * __restrict__ out)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ns) return;
-    out[k] = n > 0 ? sorted[(int)(((long long)(2 * k + 1) * n) / (2 * ns))] : ~0ull;
-}
-// next step's splitters: the key at the global position q N / world, contributed by the rank that holds it (others 0)
+// splitters of the NEXT build: the key at the global position q N / world of the (replicated) sorted keys — every rank
+// computes the same values, no communication
 __global__ void k_next_splitters(const unsigned long long * __restrict__ keys_global, long long n, int world, unsigned long long * __restrict__ split)
 {
     const int q = threadIdx.x;
@@ -195,7 +193,7 @@ struct MarkSmem { int2 stack[MK_STACK]; int2 expand[32]; };
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_mark_halo(TreeDev t, DevParams P, const int * __restrict__ cells, const int * __restrict__ n_cells, int symmetric, int gravity,
+k_mark_halo(TreeDev t, DevParams P, const int * __restrict__ cells, const int * __restrict__ n_cells, int symmetric, int bits0,
             double factor, const double * __restrict__ mass_g, const double * __restrict__ dens_g /* global-view arrays */,
             int own_lo, int own_hi, unsigned char * __restrict__ flags, unsigned long long * __restrict__ d_err)
 {
@@ -228,7 +226,7 @@ k_mark_halo(TreeDev t, DevParams P, const int * __restrict__ cells, const int * 
         bh += slack;                                                  // rounding of the node centres
 
         int top = 1;
-        if (lane == 0) sm.stack[0] = make_int2(0, 1 | (gravity ? 2 : 0));
+        if (lane == 0) sm.stack[0] = make_int2(0, bits0);
         __syncwarp();
         while (top > 0) {
             const int ne = min(top, 32);

@@ -58,24 +58,26 @@ template <int DIM> __device__ __forceinline__ double h_guess(int ngb, double mas
 //   hsoft  {2/h, h^2}              gravity softening record
 struct Recs { double4 *posm, *velc, *thermo, *av; double2 *hsoft; };
 
+// p: the rank's own particles (local index i); the records are indexed by the global tree-order index off + i
 template <int DIM>
-__global__ void k_pack_recs(PSoA p, Recs r, int n, int what)
+__global__ void k_pack_recs(PSoA p, Recs r, int n, int what, int off)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int g = off + i;
     constexpr int Y = DIM >= 2 ? 1 : 0, Z = DIM >= 3 ? 2 : 0;
-    if (what & 1) r.posm[i] = make_double4(p.pos[0][i], DIM >= 2 ? p.pos[Y][i] : 0.0, DIM >= 3 ? p.pos[Z][i] : 0.0, p.mass[i]);
-    if (what & 2) r.velc[i] = make_double4(p.vel[0][i], DIM >= 2 ? p.vel[Y][i] : 0.0, DIM >= 3 ? p.vel[Z][i] : 0.0, p.sound[i]);
+    if (what & 1) r.posm[g] = make_double4(p.pos[0][i], DIM >= 2 ? p.pos[Y][i] : 0.0, DIM >= 3 ? p.pos[Z][i] : 0.0, p.mass[i]);
+    if (what & 2) r.velc[g] = make_double4(p.vel[0][i], DIM >= 2 ? p.vel[Y][i] : 0.0, DIM >= 3 ? p.vel[Z][i] : 0.0, p.sound[i]);
     if (what & 4) {
-        r.thermo[i] = make_double4(p.ene[i], p.sml[i], p.dens[i], p.pres[i]);
-        r.av[i] = make_double4(p.gradh[i], p.alpha[i], p.balsara[i], 0.0);
+        r.thermo[g] = make_double4(p.ene[i], p.sml[i], p.dens[i], p.pres[i]);
+        r.av[g] = make_double4(p.gradh[i], p.alpha[i], p.balsara[i], 0.0);
     }
 }
 
 // Gather-permute of the whole particle state by the sorted index, fused with the packing of the gather
 // records (the values are in registers anyway): replaces k_permute + k_pack_recs(7) in the tree build.
 template <int DIM>
-__global__ void k_permute_pack(PSoA s, PSoA d, Recs r, const int * __restrict__ perm, int n, int gsph)
+__global__ void k_permute_pack(PSoA s, PSoA d, Recs r, const int * __restrict__ perm, int n, int gsph, int off)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -102,10 +104,11 @@ __global__ void k_permute_pack(PSoA s, PSoA d, Recs r, const int * __restrict__ 
             for (int v = 0; v < DIM; ++v) d.grad_v[v][a][i] = s.grad_v[v][a][q];
         }
     }
-    r.posm[i] = make_double4(pos[0], pos[1], pos[2], mass);
-    r.velc[i] = make_double4(vel[0], vel[1], vel[2], sound);
-    r.thermo[i] = make_double4(ene, sml, dens, pres);
-    r.av[i] = make_double4(gradh, alpha, balsara, 0.0);
+    const int g = off + i;                  // records: global tree-order index
+    r.posm[g] = make_double4(pos[0], pos[1], pos[2], mass);
+    r.velc[g] = make_double4(vel[0], vel[1], vel[2], sound);
+    r.thermo[g] = make_double4(ene, sml, dens, pres);
+    r.av[g] = make_double4(gradh, alpha, balsara, 0.0);
 }
 
 template <int DIM> __device__ __forceinline__ void vec_from4(const double4 & q, double (&o)[DIM])

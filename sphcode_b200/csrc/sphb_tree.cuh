@@ -117,11 +117,8 @@ __global__ void k_bbox_final(const double * __restrict__ part, int nblocks, doub
 
 // ---- keys: the reference's descent, src/bhtree.cpp:163-196 -------------------------------------
 template <int DIM>
-__global__ void k_keys(PSoA p, int n, const double * __restrict__ root, int key_levels,
-                       unsigned long long * __restrict__ keys, int * __restrict__ idx)
+__device__ __forceinline__ unsigned long long key_of(const PSoA & p, int i, const double * __restrict__ root, int key_levels)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     double c[DIM], x[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d) { c[d] = root[d]; x[d] = p.pos[d][i]; }
@@ -138,7 +135,15 @@ __global__ void k_keys(PSoA p, int n, const double * __restrict__ root, int key_
         key = (key << DIM) | bits;
         edge *= 0.5;
     }
-    keys[i] = key;
+    return key;
+}
+template <int DIM>
+__global__ void k_keys(PSoA p, int i_begin, int i_end, const double * __restrict__ root, int key_levels,
+                       unsigned long long * __restrict__ keys, int * __restrict__ idx)
+{
+    const int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i_end) return;
+    keys[i] = key_of<DIM>(p, i, root, key_levels);
     idx[i]  = i;
 }
 
@@ -349,23 +354,6 @@ __global__ void k_tree_scatter(TreeBuild t, TreeDev o, int n_nodes, const double
 #define SPHB_GROUP_CELL_GRAV 4096
 #endif
 constexpr int GROUP_CELL_SPH = SPHB_GROUP_CELL_SPH, GROUP_CELL_GRAV = SPHB_GROUP_CELL_GRAV;
-
-__global__ void k_group_flags(TreeBuild t, int n_nodes, unsigned char * __restrict__ flags, int slice_len, int n, int cell_max)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_nodes) return;
-    const int cnt = t.count[i];
-    const bool small = cnt <= cell_max;
-    const bool parent_big = (i == 0) || t.count[t.parent[i]] > cell_max;
-    if (!((small && parent_big) || (!small && t.nchild[i] == 0))) return;
-    const int first = t.first[i];
-    for (int k = 0; k < cnt; k += 32) flags[first + k] = 1;
-    // multi-GPU: a rank owns the particles [r * slice_len, (r + 1) * slice_len): groups end there too
-    if (slice_len > 0) {
-        const int r0 = (first + slice_len - 1) / slice_len;
-        for (int b = r0 * slice_len; b < first + cnt && b < n; b += slice_len) flags[b] = 1;
-    }
-}
 
 // ctl[0] = next group (work counter), ctl[1] = end group, for the particle range [p_begin, p_end)
 __global__ void k_group_range(const int * __restrict__ gstart, const int * __restrict__ n_groups, int p_begin, int p_end, int * __restrict__ ctl)

@@ -109,6 +109,10 @@ SYMBOLS = {
     "sphb_synchronize": (_i, [_vp]),
     "sphb_dim": (_i, [_vp]),
     "sphb_particle_num": (_i, [_vp]),
+    "sphb_global_particle_num": (C.c_longlong, [_vp]),
+    "sphb_first_global_index": (C.c_longlong, [_vp]),
+    "sphb_halo_records": (_u64, [_vp]),
+    "sphb_migrated": (_u64, [_vp]),
     "sphb_sizeof_particle": (_sz, [_i]),
     "sphb_nccl_unique_id": (_i, [_vp]),
     "sphb_set_distributed": (_i, [_vp, _i, _i, _vp]),
@@ -204,12 +208,14 @@ class Context:
         self._ck(self.L.sphb_upload_aos(self._c, ptr, n, self.dtype.itemsize, mask))
 
     def download(self, mask=F_ALL, out=None):
+        self.n = self.local_n
         if out is None:
             out = np.zeros(self.n, dtype=self.dtype)
         self._ck(self.L.sphb_download_aos(self._c, out.ctypes.data, self.n, self.dtype.itemsize, mask))
         return out
 
     def download_raw(self, ptr, mask=F_ALL):
+        self.n = self.local_n
         self._ck(self.L.sphb_download_aos(self._c, ptr, self.n, self.dtype.itemsize, mask))
 
     @property
@@ -299,6 +305,18 @@ class Context:
         ms = (C.c_float * 8)()
         self._ck(self.L.sphb_get_timers(self._c, ms))
         return dict(zip(T_NAMES, list(ms)))
+
+    @property
+    def local_n(self):
+        """particles this rank holds now (multi-GPU: changes with migration)"""
+        return int(self.L.sphb_particle_num(self._c))
+
+    @property
+    def global_n(self): return int(self.L.sphb_global_particle_num(self._c))
+    @property
+    def halo_records(self): return int(self.L.sphb_halo_records(self._c))
+    @property
+    def migrated(self): return int(self.L.sphb_migrated(self._c))
 
     @property
     def launches(self): return int(self.L.sphb_launch_count(self._c))
