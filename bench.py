@@ -394,6 +394,15 @@ def main():
         dist.all_reduce(loc, op=dist.ReduceOp.MAX)
     n_loc_max, n_loc_min = int(loc[0].item()), int(-loc[1].item())
     halo_records, migrated = ctx.halo_records, ctx.migrated
+    # every rank's stage times (the collectives make a rank wait for the slowest one: the table shows where)
+    names = list(lib.T_NAMES)
+    st = torch.tensor([stage_ms[k] / args.steps for k in names], dtype=torch.float64, device="cuda")
+    allst = [torch.zeros_like(st) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allst, st)
+    else:
+        allst = [st]
+    stage_by_rank = {k: [round(float(a[i].item()), 3) for a in allst] for i, k in enumerate(names)}
 
     # ---- end to end through the C ABI with host buffers
     e2e = None
@@ -525,7 +534,8 @@ def main():
         "nonconverged_newton": ctx.nonconverged,
         "state_digest": digest,
         "decomposition": {"particles_per_rank_min": n_loc_min, "particles_per_rank_max": n_loc_max,
-                          "halo_records_rank0": halo_records, "migrated_rank0": migrated},
+                          "halo_records_rank0": halo_records, "migrated_rank0": migrated,
+                          "stage_ms_per_step_by_rank": stage_by_rank if world > 1 else None},
     }
     print(json.dumps(line))
     if world > 1:

@@ -234,8 +234,14 @@ int sphb_get_counters(sphb_ctx *ctx, sphb_counters *out);
 /* Device time (ms, CUDA events on the context's stream) of the most recent call of each
  * stage: index by SPHB_T_*. */
 enum { SPHB_T_TREE = 0, SPHB_T_PRE = 1, SPHB_T_FLUID = 2, SPHB_T_GRAVITY = 3,
-       SPHB_T_TIMESTEP = 4, SPHB_T_PREDICT = 5, SPHB_T_CORRECT = 6, SPHB_T_EXCHANGE = 7,
-       SPHB_T_COUNT = 8 };
+       SPHB_T_TIMESTEP = 4, SPHB_T_PREDICT = 5, SPHB_T_CORRECT = 6,
+       SPHB_T_EXCHANGE = 7,   /* multi-GPU: all communication phases of the step (sum of the four below) */
+       SPHB_T_MIGRATE = 8,    /*   particle migration (counts + ncclSend/Recv)                           */
+       SPHB_T_KEYS = 9,       /*   pull of the ranks' sorted keys                                        */
+       SPHB_T_REDUCE = 10,    /*   all-reduces of node sums, kernel sizes, h/v_sig                       */
+       SPHB_T_HALO = 11,      /*   halo marking + record pulls over NVLink                               */
+       SPHB_T_COUNT = 12 };
+/* These times include waiting for the slowest rank at the phase's first collective. */
 int sphb_enable_timers(sphb_ctx *ctx, int enable);
 int sphb_get_timers(sphb_ctx *ctx, float ms[SPHB_T_COUNT]);
 

@@ -316,9 +316,10 @@ int alloc_particles(sphb_ctx * c, int n_up)
         const size_t nr = (size_t)c->n_rec;
         SlabLayout & L = c->lay;
         L.posm = 0; L.velc = nr * 32; L.thermo = nr * 64; L.av = nr * 96; L.hsoft = nr * 128; L.keys = nr * 144;
-        c->slab_bytes = L.keys + (np + 32) * sizeof(unsigned long long);
+        L.mig = L.keys + (np + 32) * sizeof(unsigned long long);
+        c->slab_bytes = L.mig + (c->world > 1 ? np * mig_rec(c->dim) * sizeof(double) : 0);
         if (dev_alloc(c, &c->slab, c->slab_bytes, c->allocs)) return 1;
-        CK(cudaMemsetAsync(c->slab, 0, c->slab_bytes, c->stream));
+        CK(cudaMemsetAsync(c->slab, 0, L.mig, c->stream));
         c->rc.posm = reinterpret_cast<double4 *>(c->slab + L.posm); c->rc.velc = reinterpret_cast<double4 *>(c->slab + L.velc);
         c->rc.thermo = reinterpret_cast<double4 *>(c->slab + L.thermo); c->rc.av = reinterpret_cast<double4 *>(c->slab + L.av);
         c->rc.hsoft = reinterpret_cast<double2 *>(c->slab + L.hsoft);
@@ -362,10 +363,11 @@ int alloc_particles(sphb_ctx * c, int n_up)
         const int W = c->world;
         if (dev_alloc(c, &c->d_split, W + 1, c->allocs) || dev_alloc(c, &c->d_mig, 3 * W + 1 + W * W, c->allocs) ||
             dev_alloc(c, &c->mig_idx, np, c->allocs) || dev_alloc(c, &c->mig_dest, np, c->allocs) ||
-            dev_alloc(c, &c->mig_send, np * mig_rec(c->dim), c->allocs) || dev_alloc(c, &c->mig_recv, np * mig_rec(c->dim), c->allocs) ||
+            dev_alloc(c, &c->mig_recv, np * mig_rec(c->dim), c->allocs) ||
             dev_alloc(c, &c->cells_s, np + 32, c->allocs) || dev_alloc(c, &c->cells_g, np + 32, c->allocs) ||
             dev_alloc(c, &c->d_ncells, 2, c->allocs) || dev_alloc(c, &c->d_bar, 1, c->allocs)) return 1;
         CK(cudaMemsetAsync(c->d_bar, 0, sizeof(int), c->stream));
+        c->mig_send = reinterpret_cast<double *>(c->slab + c->lay.mig);
         if (open_peers(c)) return 1;
     } else {
         c->pt = PeerTab{}; c->pt.world = 1; c->pt.slab[0] = c->slab;
@@ -528,12 +530,12 @@ int group_table(sphb_ctx * c, GroupTable & gt, bool gravity = false)
 
 // ---- multi-GPU: particle migration to the owners of their keys ------------------------------------------------------------
 // On entry c->keys holds the keys of the n own particles (local order).  Particles whose key lies outside this rank's
-// splitter range are shipped to their owner (ncclSend / ncclRecv of packed records), arrivals are appended behind the
+// splitter range move to their owner (packed by destination into the slab, pulled by the receivers over NVLink), arrivals fill the leavers' slots / go behind the
 // own particles, and the leavers' keys get the leaver bit, so that the sort moves them behind everything that stays.
 // *n_sort = entries to sort, *n_new = particles this rank owns afterwards.
 template <int DIM> int migrate_t(sphb_ctx * c, int * n_sort, int * n_new)
 {
-    Timer tx(c, SPHB_T_EXCHANGE);
+    Timer tx(c, SPHB_T_EXCHANGE), ty(c, SPHB_T_MIGRATE);
     const int W = c->world, n = c->n, B = 256, key_bits = c->P.key_levels * DIM;
     int * cnt = c->d_mig, * cursor = c->d_mig + (W + 1), * soff_d = c->d_mig + (2 * W + 1), * mat = c->d_mig + (3 * W + 1);
     CK(cudaMemsetAsync(c->d_mig, 0, sizeof(int) * (2 * W + 1), c->stream));
@@ -563,15 +565,20 @@ template <int DIM> int migrate_t(sphb_ctx * c, int * n_sort, int * n_new)
         CK(cudaMemcpyAsync(soff_d, soff.data(), sizeof(int) * W, cudaMemcpyHostToDevice, c->stream));
         k_mig_pack<DIM><<<cdiv(n_leave, B), B, 0, c->stream>>>(c->cur, c->mig_idx, c->mig_dest, n_leave, soff_d, cursor, c->mig_send); LAUNCH_CHECK();
     }
-    const size_t R = mig_rec(DIM);
-    CKN(g_nccl.GroupStart());
-    for (int r = 0; r < W; ++r) {
-        if (r == c->rank) continue;
-        const int ns = soff[r + 1] - soff[r], nr = roff[r + 1] - roff[r];
-        if (ns) CKN(g_nccl.Send(c->mig_send + (size_t)soff[r] * R, (size_t)ns * R, ncclFloat64, r, c->comm, c->stream));
-        if (nr) CKN(g_nccl.Recv(c->mig_recv + (size_t)roff[r] * R, (size_t)nr * R, ncclFloat64, r, c->comm, c->stream));
+    // arrivals are PULLED out of the senders' slabs (the blocks were packed by destination; every rank knows all counts)
+    if (nccl_barrier(c)) return 1;                      // every rank's leavers are packed
+    if (n_recv > 0) {
+        MigPull mp{};
+        for (int sr = 0; sr < W; ++sr) {
+            int so = 0;
+            for (int d = 0; d < c->rank; ++d) so += hm[(size_t)sr * W + d];
+            mp.src_off[sr] = so;
+            mp.dst_off[sr] = roff[sr];
+        }
+        mp.dst_off[W] = roff[W];
+        k_mig_pull<<<std::min(cdiv((long long)n_recv * mig_rec(DIM), B), c->sm_count * 8), B, 0, c->stream>>>(c->pt, c->lay.mig, mp, mig_rec(DIM), c->mig_recv);
+        LAUNCH_CHECK();
     }
-    CKN(g_nccl.GroupEnd());
     if (n_recv > 0) {
         k_mig_unpack<DIM><<<cdiv(n_recv, B), B, 0, c->stream>>>(c->cur, c->mig_recv, n_recv, c->mig_idx, n_leave, n,
                                                                 c->d_root, c->P.key_levels, c->keys, c->idx);
@@ -583,7 +590,7 @@ template <int DIM> int migrate_t(sphb_ctx * c, int * n_sort, int * n_new)
 // pull every rank's sorted key run into keys_glob (replicated topology); pt.off must be current
 int gather_keys(sphb_ctx * c)
 {
-    Timer tx(c, SPHB_T_EXCHANGE);
+    Timer tx(c, SPHB_T_EXCHANGE), ty(c, SPHB_T_KEYS);
     if (nccl_barrier(c)) return 1;                      // every rank's keys are sorted
     k_gather_keys<<<c->sm_count * 8, 256, 0, c->stream>>>(c->pt, c->lay.keys, c->keys_glob, c->n_glob); LAUNCH_CHECK();
     return 0;
@@ -754,7 +761,7 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         // partial sums of the leaves over the own particles, summed across ranks, then the internal nodes bottom-up
         k_level_up<DIM><<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, c->rc.posm, 0, n_nodes, c->off, c->off + n, 1); LAUNCH_CHECK();
         {
-            Timer tx(c, SPHB_T_EXCHANGE);
+            Timer tx(c, SPHB_T_EXCHANGE), ty(c, SPHB_T_REDUCE);
             CKN(g_nccl.AllReduce(c->tb.msum4, c->tb.msum4, (size_t)n_nodes * 4, ncclFloat64, ncclSum, c->comm, c->stream));
         }
         for (int l = (int)c->levels.size() - 1; l >= 0; --l) {
@@ -796,7 +803,7 @@ int set_kernel(sphb_ctx * c)
     k_clear_kernel<<<cdiv(nn, 256), 256, 0, c->stream>>>(c->td); LAUNCH_CHECK();
     k_set_kernel<<<cdiv(nn, 256), 256, 0, c->stream>>>(c->td, c->gv.sml, c->off, c->off + c->n); LAUNCH_CHECK();
     if (c->world > 1) {
-        Timer tx(c, SPHB_T_EXCHANGE);
+        Timer tx(c, SPHB_T_EXCHANGE), ty(c, SPHB_T_REDUCE);
         CKN(g_nccl.AllReduce(c->td.ksize, c->td.ksize, (size_t)nn, ncclFloat64, ncclMax, c->comm, c->stream));
     }
     k_apply_ksize<<<cdiv(nn, 256), 256, 0, c->stream>>>(c->td); LAUNCH_CHECK();
@@ -810,7 +817,7 @@ int set_kernel(sphb_ctx * c)
 template <int DIM> int halo_t(sphb_ctx * c, int phase)
 {
     if (c->world == 1) return 0;
-    Timer tx(c, SPHB_T_EXCHANGE);
+    Timer tx(c, SPHB_T_EXCHANGE), ty(c, SPHB_T_HALO);
     const int grid = c->sm_count * 4;
     if (phase < 2) {
         k_mark_halo<DIM><<<grid, 128, 0, c->stream>>>(c->td, c->P, c->cells_s, c->d_ncells + 0, 0, 1, phase == 0 ? 1.0 : c->P.kernel_ratio,
@@ -860,7 +867,7 @@ template <int DIM, int KT, int SPH> int pre_t(sphb_ctx * c)
     if (c->P.use_gravity && c->n > 0) { k_grav_pack<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->cur.sml, c->rc.hsoft + c->off, c->n); LAUNCH_CHECK(); }
     c->hsoft_valid = true;
     if (c->world > 1) {
-        Timer tx(c, SPHB_T_EXCHANGE);
+        Timer tx(c, SPHB_T_EXCHANGE), ty(c, SPHB_T_REDUCE);
         CKN(g_nccl.AllReduce(c->d_scal + 1, c->d_scal + 1, 1, ncclFloat64, ncclMin, c->comm, c->stream));
     }
     if (set_kernel(c)) return 1;

@@ -28,8 +28,10 @@ struct PeerTab {
 };
 // layout of a record slab: the five record arrays, each n_pad entries long, then the rank's sorted keys
 struct SlabLayout {
-    size_t posm, velc, thermo, av, hsoft, keys;     // byte offsets
+    size_t posm, velc, thermo, av, hsoft, keys, mig;     // byte offsets
 };
+// migration pull: the block of records rank s packed for this rank sits at src_off[s] (records) of s's mig region
+struct MigPull { int src_off[MAX_WORLD]; int dst_off[MAX_WORLD + 1]; };
 
 __device__ __forceinline__ int owner_of(const PeerTab & pt, int g)
 {
@@ -118,6 +120,20 @@ __global__ void k_mig_pack(PSoA s, const int * __restrict__ list_idx, const int 
     q[12] = pack_ints(s.pid[i], s.neighbor[i]);
     q[13] = pack_ints(s.orig[i], 0);
 }
+// arrivals: read the blocks the other ranks packed for this rank out of their slabs (NVLink peer reads)
+__global__ void k_mig_pull(PeerTab pt, size_t mig_off, MigPull mp, int rec, double * __restrict__ recv)
+{
+    const long long total = (long long)mp.dst_off[pt.world] * rec;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(e / rec);
+        int s = 0;
+#pragma unroll 1
+        for (int k = 1; k < pt.world; ++k) s += (t >= mp.dst_off[k]) ? 1 : 0;
+        const double * src = reinterpret_cast<const double *>(pt.slab[s] + mig_off) + (size_t)mp.src_off[s] * rec;
+        recv[e] = __ldcv(src + (e - (long long)mp.dst_off[s] * rec));
+    }
+}
+
 // arrival t goes into the slot of this rank's t-th leaver, the rest behind the own particles (index n_own, n_own + 1, ...)
 template <int DIM>
 __global__ void k_mig_unpack(PSoA s, const double * __restrict__ buf, int count, const int * __restrict__ list_idx, int n_leave, int n_own,

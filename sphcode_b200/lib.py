@@ -20,7 +20,7 @@ F_MASS, F_DENS, F_PRES, F_ENE, F_ENE_P, F_DENE = 1 << 4, 1 << 5, 1 << 6, 1 << 7,
 F_SML, F_SOUND, F_BALSARA, F_ALPHA, F_GRADH, F_PHI = 1 << 10, 1 << 11, 1 << 12, 1 << 13, 1 << 14, 1 << 15
 F_ID, F_NEIGHBOR = 1 << 16, 1 << 17
 F_ALL = 0x3FFFF
-T_NAMES = ("tree", "pre", "fluid", "gravity", "timestep", "predict", "correct", "exchange")
+T_NAMES = ("tree", "pre", "fluid", "gravity", "timestep", "predict", "correct", "exchange", "migrate", "keys", "reduce", "halo")
 
 
 class SphbParams(C.Structure):
@@ -302,7 +302,7 @@ class Context:
     def enable_timers(self, on=True): self._ck(self.L.sphb_enable_timers(self._c, int(on)))
 
     def timers(self):
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * len(T_NAMES))()
         self._ck(self.L.sphb_get_timers(self._c, ms))
         return dict(zip(T_NAMES, list(ms)))
 
