@@ -179,6 +179,49 @@ def reference_steps(name, over, steps, warmup):
     return len(parts) * steps / dt, dt / steps * 1e3, sim.threads, kind, len(parts), p
 
 
+def stock_binary_steps(name, over):
+    """The CPU baseline BASELINE.md names: the stock `./sph <sample> <threads>` binary of the unmodified reference
+    (oracle/_ref/sph_d<DIM>, built by `make -C oracle stock` against the Boost stand-in), run in a scratch directory on the
+    shipped parameter file with N / SPHType edits, all host threads; throughput from its own "calclation time" line
+    (src/solver.cpp:313-350: the step loop only).  Two runs: one step to learn dt, then endTime = 2.5 dt (three steps)."""
+    import re
+    import shutil
+    import tempfile
+    from oracle import refsim
+    from sphcode_b200 import params as P
+    sample, base, _, _ = CONFIGS[name]
+    o = dict(base)
+    o.update(over or {})
+    dim = P.SAMPLES[sample][0]
+    exe = refsim.stock_binary_path(dim)
+    if not os.path.exists(exe):
+        return None
+    cores = host_threads()
+    d = tempfile.mkdtemp(prefix="sphb_stock_")
+    try:
+        os.makedirs(os.path.join(d, "sample", sample))
+        def run(t_end):
+            j = dict(P.SHIPPED[sample])
+            j.update(o)
+            j.update(outputDirectory=os.path.join(d, "results"), endTime=t_end, outputTime=1e9, energyTime=1e9)
+            json.dump(j, open(os.path.join(d, "sample", sample, sample + ".json"), "w"))
+            shutil.rmtree(os.path.join(d, "results"), ignore_errors=True)
+            r = subprocess.run([exe, sample, str(cores)], cwd=d, capture_output=True, text=True, timeout=1200)
+            if r.returncode:
+                raise RuntimeError(r.stdout[-300:] + r.stderr[-300:])
+            ms = float(re.search(r"calclation time: ([0-9.eE+-]+) ms", r.stdout).group(1))
+            logs = [f for f in os.listdir(os.path.join(d, "results")) if f.endswith(".log")]
+            text = open(os.path.join(d, "results", logs[0])).read()
+            loops = re.findall(r"loop: (\d+), time: ([0-9.eE+-]+), dt: ([0-9.eE+-]+), num: (\d+)", text)
+            return ms, int(loops[-1][0]), float(loops[-1][2]), int(loops[-1][3])
+        _, _, dt, _ = run(1e-12)
+        ms, loops, _, n = run(2.5 * dt)
+        return {"value": n * loops / (ms * 1e-3), "unit": "particle-steps/s", "cores": cores, "steps": loops, "particles": n,
+                "calclation_time_ms": ms, "command": f"oracle/_ref/sph_d{dim} {sample} {cores}  (N={o['N']}, endTime=2.5 dt, no snapshots after t=0)"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -206,6 +249,10 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["cpu_baseline"]["stock_sph_binary"] = stock_binary_steps(args.config, ref_over)
+    except Exception as e:
+        line["cpu_baseline"]["stock_sph_binary"] = {"error": str(e)[:200]}
     print(json.dumps(line))
 
 
@@ -522,6 +569,10 @@ def main():
             cpu = {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": kind, "ms_per_step": cms, "value_per_core": v / max(cores, 1),
                    "sample": f"sample/{CONFIGS[args.config][0]} generator N={(ref_over or CONFIGS[args.config][1])['N']} ({nref} particles), 2 Solver::integrate steps "
                              f"after Solver::initialize + 1 warm-up, OpenMP threads={cores} (set explicitly)"}
+            try:
+                cpu["stock_sph_binary"] = stock_binary_steps(args.config, ref_over)
+            except Exception as e:
+                cpu["stock_sph_binary"] = {"error": str(e)[:200]}
         except Exception as e:  # the checker libraries did not travel
             cpu = {"value": None, "unit": "particle-steps/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
 

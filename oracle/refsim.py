@@ -277,3 +277,77 @@ class RefSim:
         out = np.zeros(2 + self.dim)
         self._f["kernel_eval"](self._c, rij.ctypes.data, float(h), out.ctypes.data)
         return out[0], out[1], out[2:]
+
+
+# ---- the whole unmodified reference Solver (oracle/ref_solver_driver.cpp, built by `make -C oracle stock`) ---------------
+class RefSolverParams(C.Structure):
+    _fields_ = [
+        ("t_start", C.c_double), ("t_end", C.c_double), ("t_output", C.c_double), ("t_energy", C.c_double),
+        ("sph_type", C.c_int), ("kernel", C.c_int),
+        ("cfl_sound", C.c_double), ("cfl_force", C.c_double), ("av_alpha", C.c_double),
+        ("use_balsara", C.c_int), ("use_tdav", C.c_int),
+        ("alpha_max", C.c_double), ("alpha_min", C.c_double), ("epsilon_av", C.c_double),
+        ("use_ac", C.c_int), ("alpha_ac", C.c_double),
+        ("max_tree_level", C.c_int), ("leaf_particle_num", C.c_int), ("neighbor_number", C.c_int),
+        ("gamma", C.c_double),
+        ("iterative_sml", C.c_int), ("periodic", C.c_int),
+        ("range_max", C.c_double * 3), ("range_min", C.c_double * 3),
+        ("use_gravity", C.c_int), ("G", C.c_double), ("theta", C.c_double),
+        ("gsph_2nd_order", C.c_int), ("n_side", C.c_int), ("sample", C.c_int),
+        ("output_dir", C.c_char * 512),
+    ]
+
+
+def solver_lib_path(dim):
+    return os.path.join(_HERE, "_ref", f"libsphsolver_d{dim}.so")
+
+
+def stock_binary_path(dim):
+    """oracle/_ref/sph_d<dim>: the stock `./sph <sample> <threads>` of the reference (CPU baseline of BASELINE.md)."""
+    return os.path.join(_HERE, "_ref", f"sph_d{dim}")
+
+
+class RefSolver:
+    """sph::Solver of the unmodified reference: Solver::read_parameterfile on `arg` (a sample name or a parameter
+    file, resolved against the CURRENT directory like the reference does) and, on demand, its sample generator."""
+
+    def __init__(self, arg, dim):
+        path = solver_lib_path(dim)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle stock` (needs /root/reference)")
+        L = C.CDLL(path)
+        L.refsolver_create.restype, L.refsolver_create.argtypes = C.c_void_p, [C.c_char_p]
+        L.refsolver_destroy.argtypes = [C.c_void_p]
+        L.refsolver_error.restype, L.refsolver_error.argtypes = C.c_char_p, [C.c_void_p]
+        L.refsolver_get_params.argtypes = [C.c_void_p, C.POINTER(RefSolverParams)]
+        L.refsolver_make_ic.argtypes = [C.c_void_p]
+        L.refsolver_get_particles.argtypes = [C.c_void_p, C.c_void_p]
+        assert L.refsolver_dim() == dim
+        self._L, self.dim = L, dim
+        self._s = L.refsolver_create(str(arg).encode())
+        err = L.refsolver_error(self._s)
+        if err:
+            msg = err.decode()
+            self.close()
+            raise RuntimeError(msg)
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self._L.refsolver_destroy(self._s)
+            self._s = None
+
+    __del__ = close
+
+    @property
+    def params(self):
+        p = RefSolverParams()
+        assert self._L.refsolver_get_params(self._s, C.byref(p)) == 0
+        return p
+
+    def initial_condition(self):
+        n = self._L.refsolver_make_ic(self._s)
+        if n < 0:
+            raise RuntimeError(self._L.refsolver_error(self._s).decode())
+        out = np.empty(n, dtype=particle_dtype(self.dim))
+        self._L.refsolver_get_particles(self._s, out.ctypes.data)
+        return out

@@ -27,8 +27,10 @@ constexpr int NW_STACK = 512;      // node stack entries per warp
 struct NWalkSmem {
     int     stack[NW_STACK];       // child0 | (nchild - 1) << 29: all children of a hit node
     int     expand[32];            // nodes of the batch being fetched
-    float4  tile32[32];            // staged candidates: {x - ref, y - ref, z - ref, symmetric threshold} in FP32
-    int     tilej[32];             //   particle index
+    int     raw[32];               // particle indices of the hit leaves, 32 at a time, before staging
+    float4  tile32[64];            // staged candidates that can be within reach of some lane (two blocks of 32, used as a ring):
+                                   //   {x - ref, y - ref, z - ref, symmetric threshold} in FP32, scaled
+    int     tilej[64];             //   particle index
 };
 
 // error bits reported through d_err[2]
@@ -98,14 +100,18 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
         F.thr = valid ? (float)(hh * hh * (1.0 + 4e-6)) : -1.0f;
     }
 
-    int fill = 0;                                        // staged candidates in the current tile
+    int fill = 0;                                        // raw indices waiting to be staged
+    int st0 = 0, nst = 0;                                // ring of staged candidates: block start (0 or 32), entries
+    const unsigned lt_mask = (1u << lane) - 1u;
 
+    // every lane tests the m staged candidates of the block at st0 (conservative FP32 test) and hands its hits on
     auto process = [&](int m) {
+        const float4 * tile = sm.tile32 + st0;
         unsigned hits = 0;
         if (P.periodic) {
 #pragma unroll 8
             for (int k = 0; k < m; ++k) {
-                const float4 c = sm.tile32[k];
+                const float4 c = tile[k];
                 float ax = fabsf(F.fi[0] - c.x);
                 ax = fminf(ax, F.L[0] - ax);
                 float r2 = ax * ax;
@@ -117,7 +123,7 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
         } else {
 #pragma unroll 8
             for (int k = 0; k < m; ++k) {
-                const float4 c = sm.tile32[k];
+                const float4 c = tile[k];
                 const float dx = F.fi[0] - c.x;
                 float r2 = dx * dx;
                 if (DIM >= 2) { const float dy = F.fi[DIM >= 2 ? 1 : 0] - c.y; r2 = fmaf(dy, dy, r2); }
@@ -130,16 +136,21 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
         while (hits) {
             const int kb = __ffs(hits) - 1;
             hits &= hits - 1;
-            v.hit(sm.tilej[kb]);
+            v.hit(sm.tilej[st0 + kb]);
         }
-        __syncwarp();                                    // the tile is refilled next: every lane is done reading it
+        __syncwarp();                                    // the block is refilled later: every lane is done reading it
     };
 
-    // FP32 image of the m candidates whose indices sit in sm.tilej
+    // FP32 image of the m raw candidates; those that cannot be within reach of ANY lane of the group (the hit leaves
+    // stick out of the group's search region by up to a leaf edge: about half of them) are dropped here, the rest is
+    // appended to the ring, and a full block of 32 is tested
     auto stage = [&](int m) {
         __syncwarp();
+        bool keep = false;
+        float4 f = make_float4(0.f, 0.f, 0.f, -1.0f);
+        int j = 0;
         if (lane < m) {
-            const int j = sm.tilej[lane];
+            j = sm.raw[lane];
             const double4 pj = ldg4(&posm[j]);
             double dj[DIM];
             dj[0] = pj.x - F.ref[0];
@@ -151,31 +162,43 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
                 if (P.periodic) dj[d] = min_image(dj[d], P.range[d]);
                 amax = fmax(amax, fabs(dj[d]));
             }
-            float4 f = make_float4((float)(dj[0] * F.sc), DIM >= 2 ? (float)(dj[DIM >= 2 ? 1 : 0] * F.sc) : 0.f,
-                                   DIM >= 3 ? (float)(dj[DIM >= 3 ? 2 : 0] * F.sc) : 0.f, -1.0f);
+            f = make_float4((float)(dj[0] * F.sc), DIM >= 2 ? (float)(dj[DIM >= 2 ? 1 : 0] * F.sc) : 0.f,
+                            DIM >= 3 ? (float)(dj[DIM >= 3 ? 2 : 0] * F.sc) : 0.f, -1.0f);
             if (SYM) {
+                // a hit needs r < max(h_i, h_j), hence |x_j - ref|_inf < bhmax + max(reach, h_j)
                 const double hj = __ldg(hj_src + (size_t)j * hj_stride);
+                keep = amax <= (bhmax + fmax(reach, hj)) * 1.001 + slack;
                 const double dl = 1.1920929e-7 * (fmax(amax, F.rlim) + lmax);
                 const double hh = (hj + 4.0 * (dl + F.delta)) * F.sc;
                 f.w = (float)(hh * hh * (1.0 + 4e-6));   // +inf for an h_j beyond FP32 range: passes (conservative)
-            } else if (amax > F.rlim) {
-                f.x = 3e18f;                         // scaled units: lanes sit in (-2, 2), thresholds <= 4: cannot pass
+            } else {
+                keep = amax <= F.rlim;                   // farther than rlim from ref: not within h_search of any lane
             }
-            sm.tile32[lane] = f;
         }
+        const unsigned kb = __ballot_sync(SPHB_FULL_MASK, keep);
+        if (keep) {
+            const int pos = (st0 + nst + __popc(kb & lt_mask)) & 63;
+            sm.tile32[pos] = f;
+            sm.tilej[pos] = j;
+        }
+        nst += __popc(kb);
         __syncwarp();
+        if (nst >= 32) {
+            process(32);
+            st0 ^= 32;
+            nst -= 32;
+        }
     };
-    // queue the particles [first, first + count) of a hit leaf; full tiles are staged and tested
+    // queue the particles [first, first + count) of a hit leaf; 32 raw indices at a time are staged
     auto feed = [&](int first, int count) {
         int off = 0;
         while (off < count) {
             const int take = min(count - off, 32 - fill);
-            if (lane < take) sm.tilej[fill + lane] = first + off + lane;
+            if (lane < take) sm.raw[fill + lane] = first + off + lane;
             fill += take;
             off += take;
             if (fill == 32) {
                 stage(32);
-                process(32);
                 fill = 0;
             }
         }
@@ -183,7 +206,6 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
 
     // ---- breadth-first descent, one lane per node.  A stack entry stands for all (contiguous)
     // children of a hit node: a batch of <= 32 nodes pushes <= 32 entries and pops >= 32 / 2^DIM.
-    const unsigned lt_mask = (1u << lane) - 1u;
     int top = 1;
     if (lane == 0) sm.stack[0] = 0;                      // the root alone: child0 = 0, nchild = 1
     __syncwarp();
@@ -257,10 +279,8 @@ __device__ __forceinline__ void group_stream(const TreeDev & t, const DevParams 
             feed(f0, c0);
         }
     }
-    if (fill > 0) {
-        stage(fill);
-        process(fill);
-    }
+    if (fill > 0) stage(fill);
+    if (nst > 0) process(nst);
     __syncwarp();
 }
 

@@ -15,7 +15,7 @@
 // SPHType) without editing the file, `--no-snapshots` keeps only energy.dat, `--binary-snapshots` writes
 // NNNNN.bin (full-precision SPHParticle records behind a 32-byte header {"SPHB", dim, n, record bytes, time})
 // next to the 6-digit text files, `--steps n` stops after n steps, `--dump-ic file` writes the initial
-// SPHParticle array (binary) and exits without touching a GPU.
+// SPHParticle array (binary) and `--dump-params file` the resolved parameters (text); both exit without touching a GPU.
 // "threads" is accepted and only used for the host-side generators.
 #include <algorithm>
 #include <chrono>
@@ -621,7 +621,7 @@ std::string fmt(const char * f, ...)
 int main(int argc, char ** argv)
 {
     std::cout << "--------------SPH simulation-------------\n\n";
-    std::string target, dump_ic;
+    std::string target, dump_ic, dump_params;
     std::vector<std::pair<std::string, std::string>> overrides;
     bool snapshots = true, binary = false;
     long max_steps = -1;
@@ -638,6 +638,7 @@ int main(int argc, char ** argv)
         else if (s == "--steps" && a + 1 < argc) max_steps = std::atol(argv[++a]);
         else if (s == "--device" && a + 1 < argc) device = std::atoi(argv[++a]);
         else if (s == "--dump-ic" && a + 1 < argc) dump_ic = argv[++a];
+        else if (s == "--dump-params" && a + 1 < argc) dump_params = argv[++a];
         else if (target.empty()) target = s;
         else threads = std::atoi(s.c_str());
     }
@@ -655,6 +656,22 @@ int main(int argc, char ** argv)
     Log log;
     try {
         const Run run = resolve(target, overrides);
+        if (!dump_params.empty()) {
+            // the resolved SPHParameters (+ time block, N, output directory), one "key value" per line, doubles with 17 digits:
+            // compared with the reference's own Solver::read_parameterfile by tests/test_host_cpu.py
+            std::ofstream f(dump_params);
+            const sphb_params & P = run.p;
+            f << "outputDirectory " << run.output_dir << "\n";
+            f << fmt("startTime %.17g\nendTime %.17g\noutputTime %.17g\nenergyTime %.17g\n", run.t_start, run.t_end, run.t_output, run.t_energy);
+            f << fmt("N %d\nsph_type %d\nkernel %d\ncfl_sound %.17g\ncfl_force %.17g\nav_alpha %.17g\n", run.n_side, P.sph_type, P.kernel, P.cfl_sound, P.cfl_force, P.av_alpha);
+            f << fmt("use_balsara_switch %d\nuse_time_dependent_av %d\nalpha_max %.17g\nalpha_min %.17g\nepsilon_av %.17g\n", P.use_balsara_switch,
+                     P.use_time_dependent_av, P.alpha_max, P.alpha_min, P.epsilon_av);
+            f << fmt("use_ac %d\nalpha_ac %.17g\nmax_tree_level %d\nleaf_particle_num %d\nneighbor_number %d\niterative_sml %d\ngamma %.17g\n", P.use_ac, P.alpha_ac,
+                     P.max_tree_level, P.leaf_particle_num, P.neighbor_number, P.iterative_sml, P.gamma);
+            f << fmt("periodic %d\nuse_gravity %d\nG %.17g\ntheta %.17g\ngsph_2nd_order %d\n", P.periodic, P.use_gravity, P.G, P.theta, P.gsph_2nd_order);
+            for (int d = 0; d < run.sample->dim; ++d) f << fmt("range_max%d %.17g\nrange_min%d %.17g\n", d, P.range_max[d], d, P.range_min[d]);
+            if (dump_ic.empty()) return 0;
+        }
         Particles q;
         make_initial_condition(run, q);
         if (!dump_ic.empty()) {
