@@ -911,7 +911,7 @@ template <int DIM, int KT, int SPH> int force_t(sphb_ctx * c)
     if (refresh_for_forces(c)) return 1;
     GroupTable gt;
     if (group_table(c, gt)) return 1;
-    k_fluid_force<DIM, KT, SPH><<<c->pre_grid, 128, 0, c->stream>>>(c->gv, c->rc, c->td, c->P, gt,
+    k_fluid_force<DIM, KT, SPH><<<std::min(c->pre_grid, c->sm_count * FF_BLOCKS), 128, 0, c->stream>>>(c->gv, c->rc, c->td, c->P, gt,
         c->scratch_j, c->d_scal + 0, c->d_err, c->counters_on ? c->d_cnt : nullptr);
     LAUNCH_CHECK();
     return 0;

@@ -19,7 +19,11 @@ namespace sphb {
 #ifndef SPHB_PF_BLOCKS
 #define SPHB_PF_BLOCKS 5
 #endif
-constexpr int PF_BLOCKS = SPHB_PF_BLOCKS;   // resident blocks per SM of k_pre_interaction / k_fluid_force
+constexpr int PF_BLOCKS = SPHB_PF_BLOCKS;   // resident blocks per SM of k_pre_interaction (96 registers)
+#ifndef SPHB_FF_BLOCKS
+#define SPHB_FF_BLOCKS 4
+#endif
+constexpr int FF_BLOCKS = SPHB_FF_BLOCKS;   // ... of k_fluid_force: 4 x 120 registers without spills beat 5 x 96 with 88 bytes of spills (measured)
 
 struct Counters {   // device mirror of sphb_counters (include/sphb.h), all summed over particles
     unsigned long long newton_evals, newton_iters, pre_candidates, pre_neighbors, force_pairs,
@@ -718,7 +722,7 @@ struct ForceAcc {
 };
 
 template <int DIM, int KT, int SPH>
-__global__ void __launch_bounds__(128, PF_BLOCKS)
+__global__ void __launch_bounds__(128, FF_BLOCKS)
 k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
               int * __restrict__ scratch_j, const double * __restrict__ d_dt,
               unsigned long long * __restrict__ d_err, Counters * __restrict__ cnt)
@@ -821,7 +825,10 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 //     lane runs one flattened loop over all particles of its queued leaves (packed x,y,z,m + 2/h
 //     read through L1; lanes of a warp are Morton neighbours and share these lines).
 #ifndef SPHB_GRAV_LQ
-#define SPHB_GRAV_LQ 96
+#define SPHB_GRAV_LQ 128
+#endif
+#ifndef SPHB_PP_ILP
+#define SPHB_PP_ILP 3
 #endif
 #ifndef SPHB_GV_BLOCKS
 #define SPHB_GV_BLOCKS 4
@@ -837,7 +844,8 @@ k_fluid_force(PSoA p, Recs rc, TreeDev t, DevParams P, GroupTable gt,
 #endif
 constexpr int GC_UNROLL = SPHB_GC_UNROLL;   // pairs of group cells per loop trip
 constexpr int GV_BLOCKS = SPHB_GV_BLOCKS;   // resident blocks per SM of k_gravity
-constexpr int GRAV_LQ = SPHB_GRAV_LQ;       // leaf queue depth per lane (global scratch, [entry][lane])
+constexpr int GRAV_LQ = SPHB_GRAV_LQ;       // leaf queue depth per lane (global scratch, [entry][lane]); flushed above GRAV_LQ - 64
+constexpr int PP_ILP = SPHB_PP_ILP;         // particle-particle pairs in flight per lane
 constexpr int GRAV_NEAR = 128;    // softened-pair list depth per lane (global scratch, [entry][lane])
 #ifndef SPHB_GV_STACK
 #define SPHB_GV_STACK 704
@@ -850,7 +858,8 @@ constexpr int GV_GC = SPHB_GV_GC; // list of cells accepted by the whole group, 
 struct GravSmem {
     int2     stack[GV_STACK];           // {child0 | (nchild - 1) << 29, lane mask}: the children of an opened node
     int2     expand[32];                // {node, lane mask} of the batch being fetched
-    double   pcx[GV_PC], pcy[GV_PC], pcz[GV_PC], pcm[GV_PC];   // accepted cells of the current chunk: mass centre, G * mass
+    double4  pc[GV_PC];                 // accepted cells of the current chunk: mass centre, G * mass (one 32-byte slot per cell)
+    double   box[8];                    // the group's bounding box: centre[3], half width[3], cmax (warp-uniform, read on use)
     double4  gcell[GV_GC + 1];          // cells accepted by EVERY particle of the group: mass centre, G * mass (+ pad)
     double4  mx[32];                    // mixed nodes of the current batch: mass centre + mass
     double   me2[32];                   //   edge^2
@@ -931,12 +940,20 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     unsigned pcw0 = 0, pcw1 = 0;                             // lane's accept bits over the chunk slots
     int npb = 0, nlq = 0, ngc = 0;                           // chunk slots, leaf queue entries, group cells in use
 
-    double bc[DIM], bh[DIM];
-    group_box<DIM>(ri, valid, bc, bh);
     const unsigned vmask = __ballot_sync(SPHB_FULL_MASK, valid);
-    double cmax = 0.0;
+    {
+        // bounding box of the group: warp-uniform, kept in shared memory (14 registers less across the interaction loops)
+        double bc[DIM], bh[DIM];
+        group_box<DIM>(ri, valid, bc, bh);
+        double cmax = 0.0;
 #pragma unroll
-    for (int d = 0; d < DIM; ++d) cmax = fmax(cmax, fabs(bc[d]) + bh[d]);
+        for (int d = 0; d < DIM; ++d) cmax = fmax(cmax, fabs(bc[d]) + bh[d]);
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) { sm.box[d] = bc[d]; sm.box[3 + d] = bh[d]; }
+            sm.box[6] = cmax;
+        }
+    }
 
     // ---- node stack and the batch held in registers.  A stack entry stands for ALL children of an
     // opened node (they are contiguous), so a batch of <= 32 nodes pushes <= 32 entries and pops >= 32 / NCH:
@@ -951,83 +968,6 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
     for (;;) {
         const bool last = (k == 0 && top == 0);
         // ================= interaction loops (each exists once; all lanes arrive together) =================
-        // (1) queued leaves: particle-particle sums of src/bhtree.cpp:309-317.  Pass 1 runs one flattened
-        // loop over all particles of the lane's queued leaves, two pairs in flight, with the unsoftened
-        // form and only LISTS the pairs that may be softened (r2 < max(h_i, h_leaf)^2 >= max(h_i, h_j)^2:
-        // no per-pair load of h_j); pass 2 runs the full Hernquist-Katz form over the listed pairs (it
-        // reduces to the unsoftened form for u >= 2, so listing too many is harmless).
-        if (last || __any_sync(SPHB_FULL_MASK, nlq > GRAV_LQ - 32)) {
-            int q = 0, j = 0, jend = 0;
-            double thr2 = 0.0;
-            double2 en = make_double2(0.0, 0.0);           // the entry after the current one, already loaded
-            if (nlq > 0) {
-                const double2 e = lq[0];
-                j = __double2loint(e.x); jend = j + __double2hiint(e.x); thr2 = e.y;
-                q = 1;
-                if (nlq > 1) en = lq[32];
-            }
-            // software pipeline: the records of the NEXT two pairs are loaded before the current two are used
-            bool have = j < jend, two = j + 1 < jend;
-            int j1 = two ? j + 1 : j;
-            double4 p0 = make_double4(0.0, 0.0, 0.0, 0.0), p1 = p0;
-            if (have) { p0 = ldg4(&posm[j]); p1 = ldg4(&posm[j1]); }
-            do {
-                int nnear = 0;
-                while (have && nnear <= GRAV_NEAR - 2) {
-                    const double4 c0 = p0, c1 = p1;
-                    const int cj = j, cj1 = j1;
-                    const bool ctwo = two;
-                    const double cthr2 = thr2;
-                    j += 2;
-                    if (j >= jend) {                            // next leaf: its entry is in registers already
-                        const bool more = q < nlq;
-                        j = more ? __double2loint(en.x) : 0;
-                        jend = more ? j + __double2hiint(en.x) : 0;
-                        thr2 = en.y;
-                        ++q;
-                        if (q < nlq) en = lq[q * 32];
-                    }
-                    have = j < jend; two = j + 1 < jend;
-                    j1 = two ? j + 1 : j;
-                    if (have) { p0 = ldg4(&posm[j]); p1 = ldg4(&posm[j1]); }
-                    double d0[DIM], d1[DIM];
-                    grav_rij<DIM, PERIODIC>(P, ri, c0, d0);
-                    grav_rij<DIM, PERIODIC>(P, ri, c1, d1);
-                    const double r20 = dot<DIM>(d0, d0), r21 = dot<DIM>(d1, d1);
-                    // branch-free: a possibly softened pair contributes 0 here and is listed for pass 2
-                    const bool n0 = r20 < cthr2, n1x = r21 < cthr2, n1 = ctwo && n1x;
-                    const double y0 = fast_rsqrt(n0 ? 1.0 : r20), y1 = fast_rsqrt(n1x ? 1.0 : r21);
-                    const double gm0 = n0 ? 0.0 : P.G * c0.w, gm1 = (!ctwo || n1x) ? 0.0 : P.G * c1.w;
-                    phi -= gm0 * y0;
-                    phi -= gm1 * y1;
-                    const double s0 = gm0 * y0 * (y0 * y0), s1 = gm1 * y1 * (y1 * y1);
-#pragma unroll
-                    for (int a = 0; a < DIM; ++a) { acc[a] -= d0[a] * s0; acc[a] -= d1[a] * s1; }
-                    if (n0) { nearq[nnear * 32] = cj; ++nnear; }
-                    if (n1) { nearq[nnear * 32] = cj1; ++nnear; }
-                    if (COUNT) n_pp += ctwo ? 2 : 1;
-                }
-                for (int kk = 0; kk < nnear; ++kk) {
-                    const int jn = nearq[kk * 32];
-                    const double4 pj = ldg4(&posm[jn]);
-                    const double einv_j = __ldg(&hsoft[jn]).x;
-                    double d[DIM];
-                    grav_rij<DIM, PERIODIC>(P, ri, pj, d);
-                    const double r2 = dot<DIM>(d, d);
-                    const double rinv = rsqrt(r2);              // inf at r == 0, unused there (u < 1 branch)
-                    const double r = r2 > 0.0 ? r2 * rinv : 0.0;
-                    double fi, gi, fj, gj;
-                    soft_fg_fast(r, rinv, einv_i, fi, gi);
-                    soft_fg_fast(r, rinv, einv_j, fj, gj);
-                    const double gm = P.G * pj.w;
-                    phi -= gm * (fi + fj) * 0.5;                // src/bhtree.cpp:314-315
-                    const double s = gm * (gi + gj) * 0.5;
-#pragma unroll
-                    for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
-                }
-            } while (have);                                     // only if the softened-pair list ran full
-            nlq = 0;
-        }
         // (2) accepted cells of the chunk (monopole, src/bhtree.cpp:326-330): every lane runs over ITS
         // accept bits, two cells in flight
         if (last || npb > GV_PC - 32) {
@@ -1036,15 +976,16 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
 #pragma unroll 1
             for (int blk = 0; blk < 2; ++blk) {
                 unsigned mm = blk == 0 ? pcw0 : pcw1;
-                const double * px = sm.pcx + blk * 32, * py = sm.pcy + blk * 32, * pz = sm.pcz + blk * 32, * pm = sm.pcm + blk * 32;
+                const double4 * pcs = sm.pc + blk * 32;
                 while (mm) {
                     const int e0 = __ffs(mm) - 1;
                     mm &= mm - 1;
                     const bool two = mm != 0;
                     const int e1 = two ? __ffs(mm) - 1 : e0;
                     mm &= mm - 1;                                  // stays 0 when !two
-                    const double4 c0 = make_double4(px[e0], DIM >= 2 ? py[e0] : 0.0, DIM >= 3 ? pz[e0] : 0.0, pm[e0]);
-                    const double4 c1 = make_double4(px[e1], DIM >= 2 ? py[e1] : 0.0, DIM >= 3 ? pz[e1] : 0.0, two ? pm[e1] : 0.0);
+                    const double4 c0 = pcs[e0];
+                    double4 c1 = pcs[e1];
+                    if (!two) c1.w = 0.0;
                     double d0[DIM], d1[DIM];
                     grav_rij<DIM, PERIODIC>(P, ri, c0, d0);
                     grav_rij<DIM, PERIODIC>(P, ri, c1, d1);
@@ -1086,8 +1027,6 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             ngc = 0;
             __syncwarp();
         }
-        if (last) break;
-
         // ================= the walk: classify the batch against the group's bounding box =================
         int cls = 0, child0 = 0, nchild = 0, first = 0, count = 0;
         double c[DIM], e2 = 0.0, mass = 0.0, hl2 = 0.0;
@@ -1101,13 +1040,15 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
             e2 = q2.x;
             child0 = __double2loint(q2.y); nchild = __double2hiint(q2.y);
             double dmin2 = 0.0, dmax2 = 0.0;
+            const double cmax = sm.box[6];
 #pragma unroll
             for (int d = 0; d < DIM; ++d) {
                 const double slack = 1e-13 * (cmax + fabs(c[d])) + 1e-300;
-                double dc = bc[d] - c[d];
+                const double bhd = sm.box[3 + d];
+                double dc = sm.box[d] - c[d];
                 if (PERIODIC) dc = min_image(dc, P.range[d]);
                 dc = fabs(dc);
-                const double lo = fmax(dc - bh[d] - slack, 0.0), hi = dc + bh[d] + slack;
+                const double lo = fmax(dc - bhd - slack, 0.0), hi = dc + bhd + slack;
                 dmin2 += lo * lo;
                 dmax2 += hi * hi;
             }
@@ -1164,13 +1105,8 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
         // (d) cells some lanes accept (class 1 with a partial mask: every lane of the mask; class 3: decided
         // below) get the next free chunk slots; racc = lanes that accept this lane's node
         const unsigned racc = (cls == 1 && !grp) ? mask : 0u;
-        if ((cls == 1 && !grp) || cls == 3) {
-            const int e = npb + sslot;
-            sm.pcx[e] = c[0];
-            if (DIM >= 2) sm.pcy[e] = c[DIM >= 2 ? 1 : 0];
-            if (DIM >= 3) sm.pcz[e] = c[DIM >= 3 ? 2 : 0];
-            sm.pcm[e] = P.G * mass;
-        }
+        if ((cls == 1 && !grp) || cls == 3)
+            sm.pc[npb + sslot] = make_double4(c[0], DIM >= 2 ? c[DIM >= 2 ? 1 : 0] : 0.0, DIM >= 3 ? c[DIM >= 3 ? 2 : 0] : 0.0, P.G * mass);
         // (e) opened by every lane of the mask, leaf -> per-lane queues (at most one entry per node of the
         // batch and lane: the head of the loop leaves room for 32)
         {
@@ -1185,6 +1121,98 @@ k_gravity(PSoA p, TreeDev t, DevParams P, GroupTable gt, const double4 * __restr
                 if ((m >> lane) & 1u) { lq[nlq * 32] = make_double2(pack_ints(f0, c0), fmax(h_i2, l2)); ++nlq; }
             }
         }
+        // ================= particle-particle sums of the queued leaves (src/bhtree.cpp:309-317) =================
+        // Placed here, where the batch of the walk is consumed and the next one is not fetched yet: the registers of
+        // the batch are dead, which is what lets PP_ILP pairs be in flight per lane without spills.  Pass 1 runs one
+        // flattened loop over all particles of the lane's queued leaves with the unsoftened form and only LISTS the
+        // pairs that may be softened (r2 < max(h_i, h_leaf)^2 >= max(h_i, h_j)^2: no per-pair load of h_j); pass 2
+        // runs the full Hernquist-Katz form over the listed pairs (it reduces to the unsoftened form for u >= 2, so
+        // listing too many is harmless).  A lane gets at most 64 entries between two visits of this point (the
+        // mixed leaves of this batch and the opened leaves of the next).
+        if (last || __any_sync(SPHB_FULL_MASK, nlq > GRAV_LQ - 64)) {
+            int q = 0, j = 0, jend = 0;
+            double thr2 = 0.0;
+            double2 en = make_double2(0.0, 0.0);           // the entry after the current one, already loaded
+            if (nlq > 0) {
+                const double2 e = lq[0];
+                j = __double2loint(e.x); jend = j + __double2hiint(e.x); thr2 = e.y;
+                q = 1;
+                if (nlq > 1) en = lq[32];
+            }
+            // software pipeline: the records of the NEXT PP_ILP pairs (all of one leaf) are loaded before the current ones are used
+            int nav = min(PP_ILP, jend - j);                // pairs of the coming trip, 0 = done
+            double4 pr[PP_ILP];
+#pragma unroll
+            for (int u = 0; u < PP_ILP; ++u) pr[u] = make_double4(0.0, 0.0, 0.0, 0.0);
+            if (nav > 0) {
+#pragma unroll
+                for (int u = 0; u < PP_ILP; ++u) pr[u] = ldg4(&posm[j + min(u, nav - 1)]);
+            }
+            do {
+                int nnear = 0;
+                while (nav > 0 && nnear <= GRAV_NEAR - PP_ILP) {
+                    double4 cr[PP_ILP];
+#pragma unroll
+                    for (int u = 0; u < PP_ILP; ++u) cr[u] = pr[u];
+                    const int cj = j, cn = nav;
+                    const double cthr2 = thr2;
+                    j += cn;
+                    if (j >= jend) {                            // next leaf: its entry is in registers already
+                        const bool more = q < nlq;
+                        j = more ? __double2loint(en.x) : 0;
+                        jend = more ? j + __double2hiint(en.x) : 0;
+                        thr2 = en.y;
+                        ++q;
+                        if (q < nlq) en = lq[q * 32];
+                    }
+                    nav = min(PP_ILP, jend - j);
+                    if (nav > 0) {
+#pragma unroll
+                        for (int u = 0; u < PP_ILP; ++u) pr[u] = ldg4(&posm[j + min(u, nav - 1)]);
+                    }
+                    // branch-free: a possibly softened pair contributes 0 here and is listed for pass 2
+                    bool nr[PP_ILP];
+#pragma unroll
+                    for (int u = 0; u < PP_ILP; ++u) {
+                        double d[DIM];
+                        grav_rij<DIM, PERIODIC>(P, ri, cr[u], d);
+                        const double r2 = dot<DIM>(d, d);
+                        const bool nx = r2 < cthr2;
+                        nr[u] = nx && u < cn;
+                        const double y = fast_rsqrt(nx ? 1.0 : r2);
+                        const double gm = (nx || u >= cn) ? 0.0 : P.G * cr[u].w;
+                        phi -= gm * y;
+                        const double sc = gm * y * (y * y);
+#pragma unroll
+                        for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * sc;
+                    }
+#pragma unroll
+                    for (int u = 0; u < PP_ILP; ++u) { if (nr[u]) { nearq[nnear * 32] = cj + u; ++nnear; } }
+                    if (COUNT) n_pp += cn;
+                }
+                for (int kk = 0; kk < nnear; ++kk) {
+                    const int jn = nearq[kk * 32];
+                    const double4 pj = ldg4(&posm[jn]);
+                    const double einv_j = __ldg(&hsoft[jn]).x;
+                    double d[DIM];
+                    grav_rij<DIM, PERIODIC>(P, ri, pj, d);
+                    const double r2 = dot<DIM>(d, d);
+                    const double rinv = rsqrt(r2);              // inf at r == 0, unused there (u < 1 branch)
+                    const double r = r2 > 0.0 ? r2 * rinv : 0.0;
+                    double fi, gi, fj, gj;
+                    soft_fg_fast(r, rinv, einv_i, fi, gi);
+                    soft_fg_fast(r, rinv, einv_j, fj, gj);
+                    const double gm = P.G * pj.w;
+                    phi -= gm * (fi + fj) * 0.5;                // src/bhtree.cpp:314-315
+                    const double s = gm * (gi + gj) * 0.5;
+#pragma unroll
+                    for (int a = 0; a < DIM; ++a) acc[a] -= d[a] * s;
+                }
+            } while (nav > 0);                                  // only if the softened-pair list ran full
+            nlq = 0;
+        }
+        if (last) break;
+
         // ---- fetch the next batch now: its loads are in flight during the per-lane tests
         __syncwarp();
         {
