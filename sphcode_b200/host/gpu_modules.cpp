@@ -1,5 +1,7 @@
 // gpu_modules.cpp — see gpu_modules.hpp.  Compiled against the reference's headers.
+#include <cstdlib>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -47,11 +49,19 @@ sphb_params to_c(const SPHParameters & p)
 struct Session {
     sphb_ctx * ctx = nullptr;
     bool resident = false;       // the device holds a full copy of the particle set
+    std::weak_ptr<Simulation> owner;   // the Simulation this context mirrors: a session dies with it
     ~Session() { if(ctx) sphb_destroy(ctx); }
 };
 
 std::mutex g_mutex;
 std::map<Simulation *, std::shared_ptr<Session>> g_sessions;
+
+// CUDA ordinal of the device the modules run on: SPHB_DEVICE (default 0)
+int device_ordinal()
+{
+    const char * e = std::getenv("SPHB_DEVICE");
+    return e ? std::atoi(e) : 0;
+}
 
 #define SPHB_CALL(s, call)\
     do {\
@@ -60,15 +70,25 @@ std::map<Simulation *, std::shared_ptr<Session>> g_sessions;
         }\
     } while(0)
 
-Session & session(Simulation * sim, const std::shared_ptr<SPHParameters> & param)
+// The device context of a Simulation.  Sessions are keyed by address but OWNED through a weak_ptr: when a Simulation
+// was destroyed (and another one may have been allocated at the same address) its context is dropped — never reused
+// with stale resident state — and the contexts of all expired Simulations are released on the way.
+Session & session(const std::shared_ptr<Simulation> & sim_sp, const std::shared_ptr<SPHParameters> & param)
 {
+    Simulation * sim = sim_sp.get();
     std::lock_guard<std::mutex> lock(g_mutex);
+    for(auto it = g_sessions.begin(); it != g_sessions.end();) {
+        if(it->second && it->second->owner.expired()) it = g_sessions.erase(it);
+        else ++it;
+    }
     auto & s = g_sessions[sim];
+    if(s && s->owner.lock() != sim_sp) s.reset();
     if(!s) {
         s = std::make_shared<Session>();
+        s->owner = sim_sp;
         static_assert(sizeof(SPHParticle) == (4 * DIM + 12) * 8 + 16, "SPHParticle layout (include/particle.hpp:8-33)");
         const sphb_params q = to_c(*param);
-        if(sphb_create(&q, DIM, 0, &s->ctx) != 0) {
+        if(sphb_create(&q, DIM, device_ordinal(), &s->ctx) != 0) {
             const std::string msg = sphb_last_error(nullptr);
             g_sessions.erase(sim);
             THROW_ERROR("libsphb: ", msg);
@@ -105,7 +125,7 @@ void PreInteraction::initialize(std::shared_ptr<SPHParameters> param) { m_param 
 
 void PreInteraction::calculation(std::shared_ptr<Simulation> sim)
 {
-    Session & s = session(sim.get(), m_param);
+    Session & s = session(sim, m_param);
     if(!s.resident) {
         upload(s, *sim, SPHB_F_ALL);      // includes alpha / balsara / sound set by Solver::initialize (src/solver.cpp:399-404)
         s.resident = true;
@@ -137,7 +157,7 @@ void FluidForce::initialize(std::shared_ptr<SPHParameters> param) { m_param = pa
 
 void FluidForce::calculation(std::shared_ptr<Simulation> sim)
 {
-    Session & s = session(sim.get(), m_param);
+    Session & s = session(sim, m_param);
     if(!s.resident) { upload(s, *sim, SPHB_F_ALL); s.resident = true; SPHB_CALL(s, sphb_make_tree(s.ctx)); }
     SPHB_CALL(s, sphb_set_dt(s.ctx, sim->get_dt()));
     SPHB_CALL(s, sphb_fluid_force(s.ctx));
@@ -152,7 +172,7 @@ void GravityForce::calculation(std::shared_ptr<Simulation> sim)
     if(!m_param->gravity.is_valid) {
         return;                                        // src/gravity_force.cpp:54-56
     }
-    Session & s = session(sim.get(), m_param);
+    Session & s = session(sim, m_param);
     if(!s.resident) { upload(s, *sim, SPHB_F_ALL); s.resident = true; SPHB_CALL(s, sphb_make_tree(s.ctx)); }
     SPHB_CALL(s, sphb_gravity_force(s.ctx));
     download(s, *sim, SPHB_F_ACC | SPHB_F_PHI);
@@ -163,7 +183,7 @@ void TimeStep::initialize(std::shared_ptr<SPHParameters> param) { m_param = para
 
 void TimeStep::calculation(std::shared_ptr<Simulation> sim)
 {
-    Session & s = session(sim.get(), m_param);
+    Session & s = session(sim, m_param);
     if(!s.resident) { upload(s, *sim, SPHB_F_ALL); s.resident = true; }
     SPHB_CALL(s, sphb_set_h_per_v_sig(s.ctx, sim->get_h_per_v_sig()));
     double dt = 0.0;
@@ -174,7 +194,7 @@ void TimeStep::calculation(std::shared_ptr<Simulation> sim)
 // ---- whole-step fast path ---------------------------------------------------------------------------
 void DeviceSolver::initialize(std::shared_ptr<Simulation> sim)
 {
-    Session & s = session(sim.get(), m_param);
+    Session & s = session(sim, m_param);
     upload(s, *sim, SPHB_F_ALL);
     s.resident = true;
     SPHB_CALL(s, sphb_initialize(s.ctx));
@@ -182,7 +202,7 @@ void DeviceSolver::initialize(std::shared_ptr<Simulation> sim)
 
 void DeviceSolver::integrate(std::shared_ptr<Simulation> sim)
 {
-    Session & s = session(sim.get(), m_param);
+    Session & s = session(sim, m_param);
     double dt = 0.0;
     SPHB_CALL(s, sphb_integrate(s.ctx, &dt));
     sim->set_dt(dt);
@@ -190,7 +210,7 @@ void DeviceSolver::integrate(std::shared_ptr<Simulation> sim)
 
 void DeviceSolver::download(std::shared_ptr<Simulation> sim)
 {
-    Session & s = session(sim.get(), m_param);
+    Session & s = session(sim, m_param);
     gpu::download(s, *sim, SPHB_F_ALL);
     double hpvs = 0.0;
     SPHB_CALL(s, sphb_get_h_per_v_sig(s.ctx, &hpvs));
