@@ -112,6 +112,8 @@ struct sphb_ctx {
     int * d_grp_ctl = nullptr;             // [0] work counter, [1] end group of the current kernel
     double2 * grav_lq = nullptr; int * grav_near = nullptr;   // per-warp leaf queues / softened-pair lists of the gravity walk
     bool grav_attr_set[2][2] = {{false, false}, {false, false}};   // dynamic-smem attribute set for k_gravity<DIM, PER, CNT>
+    int grav_mode = 1;                     // 1: k_gravity (one particle per lane); 2: k_gravity2 (two per lane: correct, 15 % slower, kept as
+                                           // the measured alternative — DESIGN.md section 3); environment SPHB_GRAVITY selects
     Recs rc{};                             // packed gather records, GLOBAL tree-order index (inside the slab)
     bool recs_dirty = true;                // SoA fields changed since the records were packed
 
@@ -781,7 +783,8 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         CK(cudaMemsetAsync(c->grp_flags, 0, (size_t)n + 1, c->stream));
         k_group_flags_own<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->off, c->off + n,
                                                               kind == 0 ? GROUP_CELL_SPH : GROUP_CELL_GRAV,
-                                                              dist ? (kind == 0 ? c->cells_s : c->cells_g) : nullptr, dist ? c->d_ncells + kind : nullptr);
+                                                              dist ? (kind == 0 ? c->cells_s : c->cells_g) : nullptr, dist ? c->d_ncells + kind : nullptr,
+                                                              kind == 1 && c->grav_mode == 2 ? GRAV2_GROUP : 32);
         LAUNCH_CHECK();
         if (n > 0) {
             size_t tb = c->cub_tmp_bytes;
@@ -950,6 +953,20 @@ template <int DIM> int gravity_t(sphb_ctx * c, bool direct, int k_targets = 0)
     if (refresh_for_forces(c)) return 1;
     GroupTable gt;
     if (group_table(c, gt, true)) return 1;
+    if (c->grav_mode == 2) {
+        const int smem = (int)(4 * sizeof(Grav2Smem));
+        const int grid = std::min(c->grav_grid, c->sm_count * GV2_BLOCKS);
+#define SPHB_GRAV(PER, CNT) do { \
+            bool & attr_set = c->grav_attr_set[PER ? 1 : 0][CNT ? 1 : 0];      /* per context: the attribute is per device */ \
+            if (!attr_set) { CK(cudaFuncSetAttribute(k_gravity2<DIM, PER, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_set = true; } \
+            k_gravity2<DIM, PER, CNT><<<grid, 128, smem, c->stream>>>(c->gv, c->td, c->P, gt, c->rc.posm, c->rc.hsoft, \
+                c->grav_lq, c->grav_near, c->d_cnt, c->d_err); } while (0)
+        if (c->P.periodic) { if (c->counters_on) SPHB_GRAV(true, true); else SPHB_GRAV(true, false); }
+        else               { if (c->counters_on) SPHB_GRAV(false, true); else SPHB_GRAV(false, false); }
+#undef SPHB_GRAV
+        LAUNCH_CHECK();
+        return 0;
+    }
     const int smem = (int)(4 * sizeof(GravSmem));
 #define SPHB_GRAV(PER, CNT) do { \
         bool & attr_set = c->grav_attr_set[PER ? 1 : 0][CNT ? 1 : 0];      /* per context: the attribute is per device */ \
@@ -1085,6 +1102,7 @@ int sphb_create(const sphb_params * hp, int dim, int device, sphb_ctx ** out)
     }
     P.key_levels = hp->max_tree_level;
     P.list_cap = hp->neighbor_number * 20;
+    if (const char * gm = std::getenv("SPHB_GRAVITY")) c->grav_mode = std::atoi(gm) == 2 ? 2 : 1;      // developer A/B switch
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     c->stream = c->own_stream;
     auto alloc = [&](auto ** p, size_t bytes) { void * q = nullptr; if (ok && cudaMalloc(&q, bytes) != cudaSuccess) ok = false; *p = static_cast<std::remove_reference_t<decltype(**p)> *>(q); };

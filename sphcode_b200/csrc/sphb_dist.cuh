@@ -12,7 +12,7 @@
 // sizes on the host, one launch per halo.  Which remote leaves are needed is decided against the replicated tree
 // topology by k_mark_halo (one warp per group cell of the own range).
 #pragma once
-#include "sphb_stages.cuh"
+#include "sphb_gravity2.cuh"
 
 namespace sphb {
 
@@ -177,7 +177,7 @@ __global__ void k_gather_keys(PeerTab pt, size_t keys_off, unsigned long long * 
 // As k_group_flags, for the particles [own_lo, own_hi) only: flags are indexed by (global index - own_lo); the first own
 // particle always starts a group.  Also lists the group cells that overlap the own range (k_mark_halo's work units).
 __global__ void k_group_flags_own(TreeBuild t, int n_nodes, unsigned char * __restrict__ flags, int own_lo, int own_hi, int cell_max,
-                                  int * __restrict__ cells, int * __restrict__ n_cells)
+                                  int * __restrict__ cells, int * __restrict__ n_cells, int chunk /* particles per group: 32, or 64 for k_gravity2 */)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
@@ -188,7 +188,7 @@ __global__ void k_group_flags_own(TreeBuild t, int n_nodes, unsigned char * __re
     const int first = t.first[i];
     if (first + cnt <= own_lo || first >= own_hi) return;
     if (cells) cells[atomicAdd(n_cells, 1)] = i;
-    for (int k = 0; k < cnt; k += 32) {
+    for (int k = 0; k < cnt; k += chunk) {
         const int g = first + k;
         if (g >= own_lo && g < own_hi) flags[g - own_lo] = 1;
     }

@@ -525,3 +525,25 @@ def test_interaction_counts_equal_the_reference_algorithm(name):
     kr = sim.counters()
     diff = {k: (kd[k], kr[k]) for k in kr if kd[k] != kr[k]}
     assert not diff, diff
+
+
+def test_two_particles_per_lane_gravity_kernel_is_the_same_algorithm(monkeypatch):
+    """k_gravity2 (sphb_gravity2.cuh, selected by SPHB_GRAVITY=2; not the default because it measured slower): the same
+    per-particle opening decisions — its interaction counters equal the reference algorithm's — and the same forces."""
+    from oracle import refsim
+    monkeypatch.setenv("SPHB_GRAVITY", "2")
+    for name in ("evrard_c4", "evrard_leaf1", "khi_gravity_periodic"):
+        p, parts = U.make_case(name)
+        c = _ctx(p, parts)
+        c.initialize()
+        c.enable_counters(True)
+        c.integrate()
+        kd = c.counters()
+        sim = refsim.RefSim(p, parts, p["DIM"], "port")
+        sim.initialize()
+        sim.counters()
+        sim.integrate()
+        kr = sim.counters()
+        diff = {k: (kd[k], kr[k]) for k in kr if kd[k] != kr[k]}
+        assert not diff, (name, diff)
+        U.assert_fields(c.particles, sim.particles, U.STEP_FIELDS, what=f"{name} k_gravity2 step", params=p)
