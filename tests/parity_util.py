@@ -69,6 +69,11 @@ def field_errors(got, ref):
     # the Balsara switch |div v| / (|div v| + |rot v| + 1e-4 c/h) lives in [0, 1]; where div v is pure
     # cancellation noise (uniform lattice) only its absolute value is meaningful
     out["balsara"] = float(np.max(np.abs(got["balsara"] - ref["balsara"])))
+    # ... and its sensitivity: b = |div| / den with den = |div| + |rot| + 1e-4 c/h >= 1e-4 (c/h) / (1 - b), so an error of
+    # rtol x (c/h) in div v (the bar of every other velocity-derived quantity) moves b by up to rtol x 1e4 (1 - b).  Where the
+    # flow is uniform (b ~ 0: KHI away from the shear layers) the switch amplifies the 1e-14 velocity differences of a
+    # second step by 1e4.  balsara_sens = |db| / (1 + 1e4 (1 - b)) is held to rtol where the plain difference cannot be.
+    out["balsara_sens"] = float(np.max(np.abs(got["balsara"] - ref["balsara"]) / (1.0 + 1e4 * (1.0 - np.minimum(ref["balsara"], 1.0)))))
     for f, floor in (("acc", a_scale), ("vel", c), ("vel_p", c)):
         d = vnorm(got[f] - ref[f])
         out[f] = float(np.max(d / np.maximum(vnorm(ref[f]) + floor, 1e-300)))
