@@ -22,7 +22,8 @@
 
 namespace sphb {
 
-constexpr int NW_STACK = 512;      // node stack entries per warp
+constexpr int NW_STACK = 640;      // node stack entries per warp: a batch leaves <= 2^DIM (8 - 1) * 4 = 28 entries per level behind, 28 * 21 + 32 = 620 for the
+                                   // deepest 3-D tree (maxTreeLevel 21); deeper 1-D / 2-D trees that outgrow it raise "node stack overflow"
 
 struct NWalkSmem {
     int     stack[NW_STACK];       // child0 | (nchild - 1) << 29: all children of a hit node
