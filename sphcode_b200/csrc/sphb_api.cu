@@ -827,14 +827,11 @@ template <int DIM> int halo_t(sphb_ctx * c, int phase)
                                                        c->gv.mass, c->gv.dens, c->off, c->off + c->n, c->halo_flags, c->d_err);
         LAUNCH_CHECK();
     } else {
-        k_mark_halo<DIM><<<grid, 128, 0, c->stream>>>(c->td, c->P, c->cells_s, c->d_ncells + 0, 1, 1, 1.0,
+        // symmetric search and gravity opening in ONE descent per (small) group cell: the gravity criterion from the cube of a
+        // <= 1024-particle cell opens fewer nodes than from a 4096-particle gravity cell and spreads over more warps
+        k_mark_halo<DIM><<<grid, 128, 0, c->stream>>>(c->td, c->P, c->cells_s, c->d_ncells + 0, 1, c->P.use_gravity ? 3 : 1, 1.0,
                                                        c->gv.mass, c->gv.dens, c->off, c->off + c->n, c->halo_flags, c->d_err);
         LAUNCH_CHECK();
-        if (c->P.use_gravity) {
-            k_mark_halo<DIM><<<grid, 128, 0, c->stream>>>(c->td, c->P, c->cells_g, c->d_ncells + 1, 1, 2, 1.0,
-                                                           c->gv.mass, c->gv.dens, c->off, c->off + c->n, c->halo_flags, c->d_err);
-            LAUNCH_CHECK();
-        }
     }
     if (nccl_barrier(c)) return 1;                      // the owners' records of this phase are written
     const int need_sph = phase < 2 ? (PULL_POSM | PULL_VELC | PULL_THERMO_A) : (PULL_POSM | PULL_VELC | PULL_THERMO_B);
