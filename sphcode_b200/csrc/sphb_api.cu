@@ -139,7 +139,7 @@ struct sphb_ctx {
     int * d_mig = nullptr;                 // [world + 1] leavers per destination + total, [world] cursors, [world] send offsets, [world * world] all ranks' counts
     int * mig_idx = nullptr, * mig_dest = nullptr;
     double * mig_send = nullptr, * mig_recv = nullptr;
-    int * cells_s = nullptr, * cells_g = nullptr, * d_ncells = nullptr;   // group cells overlapping the own range ([0] SPH, [1] gravity)
+    int * cells_s = nullptr, * d_ncells = nullptr;   // group cells (<= 1024 particles) overlapping the own range: work units of the halo marking
     unsigned char * halo_flags = nullptr, * halo_have = nullptr;
     int * d_bar = nullptr;
     bool orig_valid = true;                // `orig` is a permutation of the caller's buffer indices (false once particles migrated)
@@ -366,7 +366,7 @@ int alloc_particles(sphb_ctx * c, int n_up)
         if (dev_alloc(c, &c->d_split, W + 1, c->allocs) || dev_alloc(c, &c->d_mig, 3 * W + 1 + W * W, c->allocs) ||
             dev_alloc(c, &c->mig_idx, np, c->allocs) || dev_alloc(c, &c->mig_dest, np, c->allocs) ||
             dev_alloc(c, &c->mig_recv, np * mig_rec(c->dim), c->allocs) ||
-            dev_alloc(c, &c->cells_s, np + 32, c->allocs) || dev_alloc(c, &c->cells_g, np + 32, c->allocs) ||
+            dev_alloc(c, &c->cells_s, np + 32, c->allocs) ||
             dev_alloc(c, &c->d_ncells, 2, c->allocs) || dev_alloc(c, &c->d_bar, 1, c->allocs)) return 1;
         CK(cudaMemsetAsync(c->d_bar, 0, sizeof(int), c->stream));
         c->mig_send = reinterpret_cast<double *>(c->slab + c->lay.mig);
@@ -551,15 +551,18 @@ template <int DIM> int migrate_t(sphb_ctx * c, int * n_sort, int * n_new)
     for (int d = 0; d < W; ++d) { soff[d + 1] = soff[d] + hm[(size_t)c->rank * W + d]; roff[d + 1] = roff[d] + hm[(size_t)d * W + c->rank]; }
     for (int v : hm) moved_all += v;
     const int n_leave = soff[W], n_recv = roff[W];
-    // every rank's new count (all ranks hold the same matrix)
+    // every rank's new count (all ranks hold the same matrix); the capacity check is made for EVERY rank by every rank, so
+    // that all of them leave with the error instead of one returning and the others waiting in the next collective
+    bool fits = true;
     for (int r = 0; r < W; ++r) {
         int out = 0, in = 0;
         for (int d = 0; d < W; ++d) { out += hm[(size_t)r * W + d]; in += hm[(size_t)d * W + r]; }
+        if ((long long)c->n_all[r] + std::max(0, in - out) > c->cap) fits = false;
         c->n_all[r] += in - out;
     }
     *n_sort = n + std::max(0, n_recv - n_leave);          // arrivals first fill the leavers' slots
     *n_new = n - n_leave + n_recv;
-    if (*n_sort > c->cap) { c->err = "domain decomposition: arrivals exceed the state capacity of this rank (load imbalance above 30 %)"; return 1; }
+    if (!fits) { c->err = "domain decomposition: arrivals exceed the state capacity of a rank (load imbalance above 30 %)"; return 1; }
     if (moved_all == 0) return 0;
     c->migrated += (uint64_t)n_leave;
     c->orig_valid = false;
@@ -783,7 +786,7 @@ template <int DIM> int make_tree_t(sphb_ctx * c)
         CK(cudaMemsetAsync(c->grp_flags, 0, (size_t)n + 1, c->stream));
         k_group_flags_own<<<cdiv(n_nodes, B), B, 0, c->stream>>>(c->tb, n_nodes, c->grp_flags, c->off, c->off + n,
                                                               kind == 0 ? GROUP_CELL_SPH : GROUP_CELL_GRAV,
-                                                              dist ? (kind == 0 ? c->cells_s : c->cells_g) : nullptr, dist ? c->d_ncells + kind : nullptr,
+                                                              (dist && kind == 0) ? c->cells_s : nullptr, (dist && kind == 0) ? c->d_ncells : nullptr,   /* halo marking works on the SPH group cells */
                                                               kind == 1 && c->grav_mode == 2 ? GRAV2_GROUP : 32);
         LAUNCH_CHECK();
         if (n > 0) {
