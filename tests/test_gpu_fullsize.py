@@ -236,7 +236,8 @@ def test_full_length_energy_history_tracks_reference(name):
     seed = env_e[env_e > 0][0] if np.any(env_e > 0) else 1.0
     amp = max(10.0, 1e-12 / seed)
     over = np.nonzero(amp * env_e > 1e-10)[0]          # a decade of margin below the bar
-    k_h = int(over[0]) if len(over) else len(env_e)
+    chaotic = env_e[-1] > 1e-6                         # the reference does not track itself to the end (evrard's bounce)
+    k_h = int(over[0]) if (chaotic and len(over)) else len(env_e)
     print(f"   tight bar (1e-9 energy, 1e-6 dt) for the first {k_h} of {len(dts)} steps; measured there {dev_e[k_h - 1]:.2e} / {dev_dt[min(k_h, len(dev_dt)) - 1]:.2e}")
     assert np.all(dev_e[:k_h] <= 1e-9), int(np.argmax(dev_e > 1e-9))
     assert np.all(dev_dt[:min(k_h, len(dev_dt))] <= 1e-6), int(np.argmax(dev_dt > 1e-6))
