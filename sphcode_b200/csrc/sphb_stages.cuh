@@ -23,7 +23,7 @@ constexpr int PF_BLOCKS = SPHB_PF_BLOCKS;   // resident blocks per SM of k_pre_i
 #ifndef SPHB_FF_BLOCKS
 #define SPHB_FF_BLOCKS 4
 #endif
-constexpr int FF_BLOCKS = SPHB_FF_BLOCKS;   // ... of k_fluid_force: 4 x 120 registers without spills beat 5 x 96 with 88 bytes of spills (measured)
+constexpr int FF_BLOCKS = SPHB_FF_BLOCKS;   // ... of k_fluid_force: 4 x 128 registers (16 bytes of spills) beat 5 x 96 with 88 bytes of spills (measured)
 
 struct Counters {   // device mirror of sphb_counters (include/sphb.h), all summed over particles
     unsigned long long newton_evals, newton_iters, pre_candidates, pre_neighbors, force_pairs,
