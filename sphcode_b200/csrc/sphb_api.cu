@@ -1233,7 +1233,14 @@ int sphb_upload_aos(sphb_ctx * c, const void * particles, int n, size_t stride, 
     const bool first = (c->n_glob == 0 || n != c->n);
     if (first) {
         if ((mask & SPHB_F_ALL) != SPHB_F_ALL) { c->err = "the first upload must use SPHB_F_ALL"; return 1; }
-        if (alloc_particles(c, n)) return 1;
+        if (alloc_particles(c, n)) {
+            // out of memory (or a failed peer mapping) half-way: drop everything, the context is empty again
+            close_peers(c);
+            free_bag(c->allocs);
+            c->cur = PSoA{}; c->alt = PSoA{}; c->rc = Recs{};
+            c->n = 0; c->n_glob = 0; c->off = 0; c->tree_valid = false;
+            return 1;
+        }
     } else if (!c->orig_valid) {
         c->err = "multi-GPU mode: particles migrated since the last download; download (which renumbers the rank's particles) before uploading into them";
         return 1;
