@@ -441,3 +441,25 @@ def test_parameter_errors_pinned_to_the_reference(name, edits, drop, text, tmp_p
     with pytest.raises(P.SPHParameterError) as ej:
         P.resolve({k: v for k, v in j.items() if k != "N"}, dim)
     assert text in str(ej.value)
+
+
+def test_bench_accounting_matches_survey():
+    """bench.py's algorithmic FLOP constants and byte counts: the DIM = 3 DISPH values are SURVEY.md 8d's (57 Newton eval,
+    78 + 57 per density / Balsara neighbour, 141 force pair, 78 / 15 gravity pair / cell; 140 / 152 B per particle), the
+    other formulations follow the same counting rule; every --config resolves to the BASELINE workload it names."""
+    sys.path.insert(0, U.ROOT)
+    import bench
+    k = bench.flop_constants(3, "disph", True)
+    assert (k["newton"], k["dens"], k["bal"], k["pair"], k["pp"], k["pc"]) == (57, 78, 57, 141, 78, 15)
+    b = bench.alg_bytes(3, True)
+    assert (b["pre"], b["fluid"], b["gravity"]) == (140, 152, 120)
+    assert bench.flop_constants(2, "gsph", True)["pair"] == 207 and bench.flop_constants(2, "disph", True)["pair"] == 123
+    assert bench.flop_constants(1, "ssph", True)["bal"] == 0            # no Balsara loop in 1-D (src/pre_interaction.cpp:106)
+    expect = {"c1": ("shock_tube", 1, 50), "c2": ("khi", 2, 1152), "c3": ("gresho_chan_vortex", 2, 2048), "c4": ("evrard", 3, 124),
+              "c5": ("evrard", 3, 312), "c5_64m": ("evrard", 3, 496)}
+    for name, (sample, dim, n) in expect.items():
+        p = bench.config_params(name)
+        assert (p["sample"], p["DIM"], p["N"]) == (sample, dim, n), name
+    assert bench.config_params("c2")["SPHType"] == "disph" and bench.config_params("c2")["useArtificialConductivity"]
+    assert bench.config_params("c3")["SPHType"] == "gsph" and bench.config_params("c3")["use2ndOrderGSPH"]
+    assert bench.config_params("c5")["useGravity"] and bench.config_params("c5")["theta"] == 0.5
