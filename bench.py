@@ -18,7 +18,7 @@ value      whole-job particle-steps/s, state resident in HBM, CUDA events on the
 e2e        the same step through the C ABI with HOST buffers, every step: sphb_upload_aos (pinned host AoS of the
            rank's particles -> device) + sphb_integrate + sphb_download_aos inside the timed region.
 e2e.module the reference's module sequence with only the members Solver::predict / correct write going up
-           (src/solver.cpp:442-455) and only what each module writes coming down (field masks, in place over PCIe).
+           (src/solver.cpp:442-455) and only what each module writes coming down (field masks).
 roofline   the dominant kernel of the step (the stage with the largest device time): algorithmic FP64 FLOPs of the
            REFERENCE algorithm on this input (hand-counted constants of SURVEY.md 8d x interaction counts taken by
            the kernels' own counters in an untimed step) / its CUDA-event duration, against the FP64 FMA peak of this

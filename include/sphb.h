@@ -131,11 +131,12 @@ int sphb_set_distributed_id(sphb_ctx *ctx, int rank, int world, const void *uniq
 /* Host AoS -> device.  First call (or a different n) sizes the context (BHTree::resize,
  * src/bhtree.cpp:42-53).  `stride` = bytes between records (>= sphb_sizeof_particle(dim)).
  * field_mask selects which members are taken from the host copy; the first upload must
- * use SPHB_F_ALL.  With a partial mask and a pinned / registered host buffer (sphb_host_alloc,
- * cudaHostRegister) the selected members are read in place over PCIe — nothing else moves. */
+ * use SPHB_F_ALL.  With a partial mask, a pinned / registered host buffer (sphb_host_alloc,
+ * cudaHostRegister) and fewer than 2^18 records the selected members are read in place over PCIe;
+ * larger sets go through a whole-record DMA and a masked unpack on the device. */
 int sphb_upload_aos(sphb_ctx *ctx, const void *particles, int n, size_t stride, uint32_t field_mask);
-/* Device -> host AoS; only members in field_mask are written (pinned / registered buffer and a
- * partial mask: written in place over PCIe by the pack kernel, no staging and no host pass). */
+/* Device -> host AoS; only members in field_mask are written (partial mask: small sets in pinned /
+ * registered memory in place over PCIe by the pack kernel, larger ones by a staged DMA + host threads). */
 int sphb_download_aos(sphb_ctx *ctx, void *particles, int n, size_t stride, uint32_t field_mask);
 
 /* GSPH MUSCL gradient arrays, Simulation::get_vector_array(name) (src/simulation.cpp:68-76):
