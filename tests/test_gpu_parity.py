@@ -547,3 +547,36 @@ def test_two_particles_per_lane_gravity_kernel_is_the_same_algorithm(monkeypatch
         diff = {k: (kd[k], kr[k]) for k in kr if kd[k] != kr[k]}
         assert not diff, (name, diff)
         U.assert_fields(c.particles, sim.particles, U.STEP_FIELDS, what=f"{name} k_gravity2 step", params=p)
+
+
+def test_masked_transfers_in_place_on_pinned_memory():
+    """Partial-mask upload / download with a PINNED host buffer (sphb_host_alloc) and a small set: the pack / unpack
+    kernels read and write the selected members of the caller's SPHParticle records in place over PCIe; everything else
+    in the buffer stays untouched, and the result equals the staged path's (pageable numpy buffer)."""
+    import ctypes
+    from sphcode_b200 import lib
+    p, parts = U.make_case("evrard_c4")
+    n, rec = len(parts), parts.dtype.itemsize
+    c = _ctx(p, parts)
+    c.initialize()
+    full = c.particles
+    h = c.L.sphb_host_alloc(n * rec)
+    assert h
+    try:
+        view = np.ctypeslib.as_array(ctypes.cast(h, ctypes.POINTER(ctypes.c_ubyte)), shape=(n * rec,)).view(parts.dtype)
+        view[:] = 0
+        view["mass"] = -7.0                                            # a member outside the mask: must survive the download
+        c.download_raw(h, lib.F_DENS | lib.F_ACC | lib.F_NEIGHBOR)
+        assert np.array_equal(view["dens"], full["dens"]) and np.array_equal(view["acc"], full["acc"])
+        assert np.array_equal(view["neighbor"], full["neighbor"])
+        assert np.all(view["mass"] == -7.0) and not view["pos"].any() and not view["id"].any()
+        view[:] = full
+        view["vel"] += 2.0
+        view["ene"] *= 3.0
+        view["dens"] = -1.0                                            # outside the upload mask: must not reach the device
+        c.upload_raw(h, n, lib.F_VEL | lib.F_ENE)
+        back = c.particles
+        assert np.array_equal(back["vel"], full["vel"] + 2.0) and np.array_equal(back["ene"], full["ene"] * 3.0)
+        assert np.array_equal(back["dens"], full["dens"]) and np.array_equal(back["pos"], full["pos"])
+    finally:
+        c.L.sphb_host_free(h)
